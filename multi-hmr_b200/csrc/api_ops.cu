@@ -1,0 +1,31 @@
+// Stage-level C-ABI entry points (unit parity + ncu targets). See include/mhmr.h.
+#include "../../include/mhmr.h"
+#include "gemm_tc.cuh"
+
+using namespace mhmr;
+
+extern "C" {
+
+const char* mhmr_last_error(void) { return get_last_error(); }
+
+int mhmr_op_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                     int epilogue, const float* bias, const float* gamma, const float* rowadd,
+                     void* out, int64_t ldo, int rows_in, int rows_out, int row_off, int block_n,
+                     void* stream) {
+  GemmEpi ep;
+  ep.bias = bias;
+  ep.gamma = gamma;
+  ep.rowadd = rowadd;
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.rows_in = rows_in;
+  ep.rows_out = rows_out;
+  ep.row_off = row_off;
+  GemmPlan plan;
+  int rc = gemm_plan_init(&plan, static_cast<const __half*>(A), lda, static_cast<const __half*>(W),
+                          ldw, M, N, K, epilogue, ep, block_n);
+  if (rc != MHMR_OK) return rc;
+  return gemm_plan_run(&plan, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

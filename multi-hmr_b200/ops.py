@@ -1,0 +1,36 @@
+"""Stage-level operators of libmhmr_sm100.so as torch-tensor functions (unit parity + ncu targets).
+
+Each function borrows the tensors' device pointers for the duration of the call and launches on the
+current torch CUDA stream.  There is no CPU path: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import c_int, c_int64, check, ptr, stream_ptr
+
+EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RELU_F16, EPI_LS_RESID_F32, EPI_ROWADD_F32, EPI_BIAS_F32 = range(6)
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("multihmr_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def gemm_f16(a, w, epilogue, out, bias=None, gamma=None, rowadd=None, rows_in=0, rows_out=0, row_off=0,
+             block_n=256):
+    """out = epilogue(a[M,K] @ w[N,K]^T); a, w fp16 with contiguous K. `out` is written in place."""
+    _cuda(a, w, out, bias, gamma, rowadd)
+    assert a.dtype == torch.float16 and w.dtype == torch.float16
+    assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    lib = _lib.load()
+    rc = lib.mhmr_op_gemm_f16(ptr(a), c_int64(a.stride(0)), ptr(w), c_int64(w.stride(0)), c_int(M), c_int(N),
+                              c_int(K), c_int(epilogue), ptr(bias), ptr(gamma), ptr(rowadd), ptr(out),
+                              c_int64(out.stride(0)), c_int(rows_in), c_int(rows_out), c_int(row_off),
+                              c_int(block_n), stream_ptr())
+    check(rc, "mhmr_op_gemm_f16")
+    return out

@@ -1,0 +1,120 @@
+"""tcgen05 GEMM family vs plain torch fp32 on the same fp16-rounded operands (floating-point kernel:
+torch fp32 reference, see task ③).  Tolerances are stated per test."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_linear(a16, w16):
+    return a16.float() @ w16.float().t()
+
+
+SHAPES = [
+    # (M, N, K): multiples, M tails, K tails (588 -> padded 592), ViT-S dims, big
+    (128, 256, 64),
+    (256, 256, 128),
+    (300, 1024, 1024),
+    (4097, 3072, 1024),
+    (2305, 384, 1536),
+    (1000, 1152, 384),
+    (513, 1024, 592),
+    (4096, 1024, 1152),
+    (64, 32, 1024),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_bias_f16(cuda_device, M, N, K, bn):
+    from multihmr_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, generator=g) * 1.0).to(cuda_device).half()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(cuda_device).half()
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    out = torch.empty(M, N, device=cuda_device, dtype=torch.float16)
+    ops.gemm_f16(a, w, ops.EPI_BIAS_F16, out, bias=bias, block_n=bn)
+    ref = _ref_linear(a, w) + bias
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    # fp32 accumulate of exact fp16 products, then one fp16 rounding of the output: 2^-11 relative
+    assert err <= 1e-3 * max(scale, 1.0) + 1e-3, (err, scale)
+
+
+@pytest.mark.parametrize("epi", ["gelu", "relu"])
+def test_gemm_act_f16(cuda_device, epi):
+    from multihmr_b200 import ops
+
+    M, N, K = 1537, 4096, 1024
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = torch.randn(M, K, generator=g).to(cuda_device).half()
+    w = (torch.randn(N, K, generator=g) * 0.03).to(cuda_device).half()
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    out = torch.empty(M, N, device=cuda_device, dtype=torch.float16)
+    kind = ops.EPI_BIAS_GELU_F16 if epi == "gelu" else ops.EPI_BIAS_RELU_F16
+    ops.gemm_f16(a, w, kind, out, bias=bias)
+    pre = _ref_linear(a, w) + bias
+    ref = torch.nn.functional.gelu(pre) if epi == "gelu" else torch.relu(pre)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), err
+
+
+def test_gemm_layerscale_residual_f32(cuda_device):
+    from multihmr_b200 import ops
+
+    M, N, K = 4097 * 2, 1024, 4096
+    g = torch.Generator(device="cpu").manual_seed(11)
+    a = torch.randn(M, K, generator=g).to(cuda_device).half()
+    w = (torch.randn(N, K, generator=g) * 0.02).to(cuda_device).half()
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    gamma = torch.rand(N, generator=g).to(cuda_device)
+    x0 = torch.randn(M, N, generator=g).to(cuda_device)
+    x = x0.clone()
+    ops.gemm_f16(a, w, ops.EPI_LS_RESID_F32, x, bias=bias, gamma=gamma)
+    ref = x0 + gamma * (_ref_linear(a, w) + bias)
+    err = (x - ref).abs().max().item()
+    # fp32 everywhere after the exact fp16 products: only summation-order noise
+    assert err <= 2e-4, err
+
+
+def test_gemm_rowadd_remap_f32(cuda_device):
+    """Patch-embed shape: rows of image b land at b*T + 1 + n, with a per-n additive table."""
+    from multihmr_b200 import ops
+
+    B, Np, D, K = 3, 2304, 384, 592
+    T = Np + 1
+    g = torch.Generator(device="cpu").manual_seed(13)
+    a = torch.randn(B * Np, K, generator=g).to(cuda_device).half()
+    w = (torch.randn(D, K, generator=g) * 0.05).to(cuda_device).half()
+    table = torch.randn(Np, D, generator=g).to(cuda_device)
+    out = torch.full((B * T, D), 7.0, device=cuda_device)
+    ops.gemm_f16(a, w, ops.EPI_ROWADD_F32, out, rowadd=table, rows_in=Np, rows_out=T, row_off=1, block_n=128)
+    ref = (_ref_linear(a, w).view(B, Np, D) + table).reshape(B, Np, D)
+    got = out.view(B, T, D)
+    assert torch.all(got[:, 0] == 7.0)  # cls rows untouched
+    err = (got[:, 1:] - ref).abs().max().item()
+    assert err <= 2e-4, err
+
+
+def test_gemm_bias_f32_nobias(cuda_device):
+    from multihmr_b200 import ops
+
+    M, N, K = 2304, 1024, 1152
+    g = torch.Generator(device="cpu").manual_seed(17)
+    a = torch.randn(M, K, generator=g).to(cuda_device).half()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(cuda_device).half()
+    out = torch.empty(M, N, device=cuda_device)
+    ops.gemm_f16(a, w, ops.EPI_BIAS_F32, out)
+    err = (out - _ref_linear(a, w)).abs().max().item()
+    assert err <= 2e-4, err
+
+
+def test_gemm_rejects_bad_args(cuda_device):
+    from multihmr_b200 import ops
+
+    a = torch.zeros(16, 64, device=cuda_device, dtype=torch.float16)
+    w = torch.zeros(48, 64, device=cuda_device, dtype=torch.float16)  # N not multiple of 32
+    out = torch.zeros(16, 48, device=cuda_device, dtype=torch.float16)
+    with pytest.raises(AssertionError):
+        ops.gemm_f16(a, w, ops.EPI_BIAS_F16, out, bias=torch.zeros(48, device=cuda_device))

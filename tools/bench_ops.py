@@ -1,0 +1,68 @@
+"""Micro-benchmarks of the stage-level operators on one B200 (CUDA events, L2-flushed)."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from multihmr_b200 import ops  # noqa: E402
+
+
+def timeit(fn, iters=10, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def bench_gemm(dev, flush):
+    res = []
+    for (M, N, K, epi, bn) in [
+        (32776, 3072, 1024, ops.EPI_BIAS_F16, 256),
+        (32776, 1024, 1024, ops.EPI_LS_RESID_F32, 256),
+        (32776, 1024, 1024, ops.EPI_LS_RESID_F32, 128),
+        (32776, 4096, 1024, ops.EPI_BIAS_GELU_F16, 256),
+        (32776, 1024, 4096, ops.EPI_LS_RESID_F32, 256),
+        (32776, 1024, 4096, ops.EPI_LS_RESID_F32, 128),
+        (32768, 1024, 1152, ops.EPI_BIAS_F32, 256),
+    ]:
+        a = torch.randn(M, K, device=dev).half()
+        w = (torch.randn(N, K, device=dev) * 0.03).half()
+        bias = torch.randn(N, device=dev)
+        gamma = torch.rand(N, device=dev)
+        f16 = epi in (ops.EPI_BIAS_F16, ops.EPI_BIAS_GELU_F16, ops.EPI_BIAS_RELU_F16)
+        out = torch.zeros(M, N, device=dev, dtype=torch.float16 if f16 else torch.float32)
+        ms = timeit(lambda: ops.gemm_f16(a, w, epi, out, bias=bias, gamma=gamma, block_n=bn), flush=flush)
+        ms_ref = timeit(lambda: torch.matmul(a, w.t()), flush=flush)
+        tf = 2.0 * M * N * K / ms / 1e9
+        res.append(dict(op="gemm", M=M, N=N, K=K, epi=epi, bn=bn, ms=round(ms, 4), tflops=round(tf, 1),
+                        cublas_ms=round(ms_ref, 4), cublas_tflops=round(2.0 * M * N * K / ms_ref / 1e9, 1)))
+        print(res[-1], flush=True)
+    return res
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="gemm")
+    ap.add_argument("--out", default="gpurun_out/bench_ops.json")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)
+    out = {}
+    for what in args.what.split(","):
+        out[what] = globals()["bench_" + what](dev, flush)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    json.dump(out, open(args.out, "w"), indent=1)
