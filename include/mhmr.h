@@ -50,6 +50,13 @@ int mhmr_op_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int
                      void* out, int64_t ldo, int rows_in, int rows_out, int row_off, int block_n,
                      void* stream);
 
+/* Multi-head self-attention of the ViT backbone, head dim 64: out[:, h*64:(h+1)*64] =
+ * softmax(q_h k_h^T / 8) v_h per image.  qkv is [B*T, 3*D] fp16 (q | k | v column blocks, the layout the
+ * qkv Linear produces), out is [B*T, D] fp16.  Replaces dinov2 Attention.forward's
+ * `q*scale @ k^T -> softmax -> @ v` (reached from reference blocks/dinov2.py:25). */
+int mhmr_op_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int B, int T, int D,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

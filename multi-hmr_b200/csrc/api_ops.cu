@@ -1,6 +1,7 @@
 // Stage-level C-ABI entry points (unit parity + ncu targets). See include/mhmr.h.
 #include "../../include/mhmr.h"
 #include "gemm_tc.cuh"
+#include "kernels.cuh"
 
 using namespace mhmr;
 
@@ -26,6 +27,12 @@ int mhmr_op_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int
                           ldw, M, N, K, epilogue, ep, block_n);
   if (rc != MHMR_OK) return rc;
   return gemm_plan_run(&plan, static_cast<cudaStream_t>(stream));
+}
+
+int mhmr_op_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int B, int T, int D,
+                      void* stream) {
+  return attention_forward(static_cast<const __half*>(qkv), ld_qkv, static_cast<__half*>(out), ldo, B, T,
+                           D, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,285 @@
+// Multi-head self-attention of the DINOv2 backbone (head dim 64) on tcgen05 tensor cores.
+//
+// Replaces `softmax(q k^T / 8) v` of dinov2 `Attention.forward` (reached from the reference at
+// blocks/dinov2.py:25).  Flash-style: the T x T score matrix never leaves the SM.
+//
+//   grid  = (ceil(T/128) query tiles, heads, images), 2 CTAs co-resident per SM
+//   CTA   = 192 threads: warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 softmax (1 thread = 1 row)
+//   TMEM  = 256 columns: S (128 fp32) | P (64 cols = 128 fp16, A operand of the PV MMA) | O (64 fp32)
+//   S = Q K^T : tcgen05.mma SS, M=128 N=128 K=64     (K tile K-major,  128B swizzle, via TMA)
+//   O += P V  : tcgen05.mma TS, M=128 N=64  K=128    (V tile MN-major, 128B swizzle, via TMA)
+// Online softmax in fp32 in the exp2 domain with lazy rescaling of O (only when the running max
+// grows by more than 2^8), so the O read-modify-write through tcgen05.ld/st is rare.
+#include "common.cuh"
+
+namespace mhmr {
+
+namespace {
+
+constexpr int kHeadDim = 64;
+constexpr int kBlockQ = 128;
+constexpr int kBlockKV = 128;
+constexpr int kStagesKV = 2;
+constexpr int kAttnThreads = 192;
+constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: Q, K or V tile
+constexpr int kAttnSmem = kTileBytes * (1 + 2 * kStagesKV) + 256 + 1024;
+
+constexpr uint32_t kColS = 0;
+constexpr uint32_t kColP = 128;
+constexpr uint32_t kColO = 192;
+constexpr int kTmemCols = 256;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
+                int T, int D, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kTileBytes;                     // [kStagesKV]
+  uint8_t* sV = smem + kTileBytes * (1 + kStagesKV);   // [kStagesKV]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTileBytes * (1 + 2 * kStagesKV));
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // [kStagesKV]
+  uint64_t* v_full = k_full + kStagesKV;   // [kStagesKV]
+  uint64_t* kv_empty = v_full + kStagesKV; // [kStagesKV]
+  uint64_t* s_full = kv_empty + kStagesKV; // MMA -> softmax : S_j complete
+  uint64_t* s_empty = s_full + 1;          // softmax -> MMA : S_j now in registers
+  uint64_t* p_full = s_empty + 1;          // softmax -> MMA : P_j in TMEM (and O rescaled)
+  uint64_t* pv_done = p_full + 1;          // MMA -> softmax : O += P_j V_j complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+  const int row0 = img * T;              // first token row of this image in the [B*T, 3D] matrix
+  const int q0 = q_tile * kBlockQ;
+  const int n_kv = (T + kBlockKV - 1) / kBlockKV;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      mbar_init(q_full, 1);
+      for (int s = 0; s < kStagesKV; ++s) {
+        mbar_init(&k_full[s], 1);
+        mbar_init(&v_full[s], 1);
+        mbar_init(&kv_empty[s], 1);
+      }
+      mbar_init(s_full, 1);
+      mbar_init(s_empty, 4);
+      mbar_init(p_full, 4);
+      mbar_init(pv_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<kTmemCols>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_2d(sQ, &tmQKV, q_full, head * kHeadDim, row0 + q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kStagesKV;
+        const uint32_t ph = (j / kStagesKV) & 1u;
+        mbar_wait(&kv_empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&k_full[s], kTileBytes);
+        tma_load_2d(sK + s * kTileBytes, &tmQKV, &k_full[s], D + head * kHeadDim, row0 + j * kBlockKV);
+        mbar_arrive_expect_tx(&v_full[s], kTileBytes);
+        tma_load_2d(sV + s * kTileBytes, &tmQKV, &v_full[s], 2 * D + head * kHeadDim,
+                    row0 + j * kBlockKV);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, false, true);  // B (V) is MN-major
+      const uint32_t t_s = tmem_base + kColS;
+      const uint32_t t_p = tmem_base + kColP;
+      const uint32_t t_o = tmem_base + kColO;
+      const uint64_t q_desc = make_sw128_desc(smem_u32(sQ), 16, 1024);
+
+      auto issue_qk = [&](int j) {
+        const int s = j % kStagesKV;
+        mbar_wait(&k_full[s], (j / kStagesKV) & 1u);
+        tc_fence_after();
+        const uint64_t k_desc = make_sw128_desc(smem_u32(sK + s * kTileBytes), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_f16_ss(t_s, q_desc + 2u * k, k_desc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+      };
+
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {
+          mbar_wait(s_empty, j & 1u);  // softmax holds S_j in registers: S may be overwritten
+          tc_fence_after();
+          issue_qk(j + 1);
+        }
+        const int s = j % kStagesKV;
+        mbar_wait(&v_full[s], (j / kStagesKV) & 1u);
+        mbar_wait(p_full, j & 1u);
+        tc_fence_after();
+        // V tile: 128 keys (K) x 64 dims (N), N contiguous: MN-major, 8-key groups 1024 B apart.
+        const uint64_t v_desc = make_sw128_desc(smem_u32(sV + s * kTileBytes), 1024, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockKV / 16; ++k) {
+          // A: 16 fp16 of P = 8 TMEM columns per K step; B: 16 keys = 2048 B per K step
+          umma_f16_ts(t_o, t_p + 8u * k, v_desc + 128u * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ------------------------------ Softmax warps ------------------------------
+    const int sub = warp & 3;  // TMEM sub-partition
+    const int row = sub * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(sub * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + kColS;
+    const uint32_t t_p = tmem_base + lane_base + kColP;
+    const uint32_t t_o = tmem_base + lane_base + kColO;
+
+    float m_used = -INFINITY;  // running max (log2 domain) actually used as the exponent offset
+    float l = 0.0f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1u);
+      tc_fence_after();
+      uint32_t s[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+
+      const int valid = T - j * kBlockKV;  // keys of this tile that exist (>= 128 except last tile)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(s[c][i]);
+          if (valid < kBlockKV && (c * 32 + i) >= valid) v = -INFINITY;
+          s[c][i] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m_used, mx * scale_log2);
+      bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile (m_used = -inf)
+      float alpha = 1.0f;
+      if (rescale) {
+        alpha = exp2f(m_used - m_new);  // 0 on the first tile
+        m_used = m_new;
+      }
+      float sum = 0.0f;
+      uint32_t p[2][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float e0 = exp2f(fmaf(__uint_as_float(s[c][i]), scale_log2, -m_used));
+          const float e1 = exp2f(fmaf(__uint_as_float(s[c][i + 1]), scale_log2, -m_used));
+          sum += e0 + e1;
+          const __half2 h = __floats2half2_rn(e0, e1);
+          p[c >> 1][(c & 1) * 16 + i / 2] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+      }
+      l = l * alpha + sum;
+
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1u);  // P buffer free, O stable
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, rescale)) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(t_o + c * 32, o);
+          }
+        }
+      }
+      tmem_st_32x32(t_p, p[0]);
+      tmem_st_32x32(t_p + 32, p[1]);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+
+    // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
+    mbar_wait(pv_done, (n_kv - 1) & 1u);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int q = q0 + row;
+    __half* dst = out + static_cast<int64_t>(row0 + q) * ldo + head * kHeadDim;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_o + c * 32, o);
+      tmem_ld_wait();
+      if (q < T) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __half2 h = __floats2half2_rn(__uint_as_float(o[g * 8 + 2 * i]) * inv_l,
+                                                __uint_as_float(o[g * 8 + 2 * i + 1]) * inv_l);
+            pw[i] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace
+
+// qkv: [B*T, 3*D] fp16 (row pitch ld_qkv), q|k|v column blocks, head h = columns h*64..h*64+63 of each.
+// out: [B*T, D] fp16 (row pitch ldo).
+int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ldo, int B, int T, int D,
+                      cudaStream_t stream) {
+  MHMR_REQUIRE(D % kHeadDim == 0, "attention: embed dim must be a multiple of 64");
+  MHMR_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0, "attention: row pitches must be multiples of 8");
+  MHMR_REQUIRE(B > 0 && T > 0, "attention: empty problem");
+  CUtensorMap tm;
+  int rc = make_tmap_2d(&tm, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<uint64_t>(B) * T,
+                        3ull * D, ld_qkv * 2, 128, 64, true);
+  if (rc != MHMR_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kAttnSmem));
+    attr_set = true;
+  }
+  const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+  dim3 grid((T + kBlockQ - 1) / kBlockQ, D / kHeadDim, B);
+  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2);
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+}  // namespace mhmr

@@ -34,3 +34,16 @@ def gemm_f16(a, w, epilogue, out, bias=None, gamma=None, rowadd=None, rows_in=0,
                               c_int(block_n), stream_ptr())
     check(rc, "mhmr_op_gemm_f16")
     return out
+
+
+def attention(qkv, B, T, D, out=None):
+    """qkv [B*T, 3*D] fp16 -> out [B*T, D] fp16, heads of 64 dims, softmax(q k^T / 8) v per image."""
+    _cuda(qkv)
+    assert qkv.dtype == torch.float16 and qkv.shape == (B * T, 3 * D) and qkv.stride(1) == 1
+    if out is None:
+        out = torch.empty(B * T, D, device=qkv.device, dtype=torch.float16)
+    lib = _lib.load()
+    rc = lib.mhmr_op_attention(ptr(qkv), c_int64(qkv.stride(0)), ptr(out), c_int64(out.stride(0)), c_int(B),
+                               c_int(T), c_int(D), stream_ptr())
+    check(rc, "mhmr_op_attention")
+    return out
