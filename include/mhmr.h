@@ -57,6 +57,88 @@ int mhmr_op_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int
 int mhmr_op_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int B, int T, int D,
                       void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Engine: the whole `Model.forward(x, K)` path (reference model.py:205-349) behind one handle
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mhmr_engine mhmr_engine;
+
+typedef struct mhmr_config {
+  int arch;              /* 0 = dinov2_vits14, 1 = dinov2_vitb14, 2 = dinov2_vitl14 (Model(backbone=...), model.py:35) */
+  int img_size;          /* Model(img_size=...), multiple of 14 (model.py:37,65) */
+  int max_batch;         /* capacity of the activation workspaces */
+  int max_persons;       /* capacity of the per-person buffers; more detections => MHMR_ERR_CAPACITY */
+  int xat_depth;         /* Model(xat_depth=...)     model.py:42 */
+  int xat_num_heads;     /* Model(xat_num_heads=...) model.py:43 */
+  int num_betas;         /* Model(num_betas=...)     model.py:47 (10 or 11) */
+  int person_center_idx; /* index of Model(person_center=...) in smplx JOINT_NAMES ('head' = 15) */
+  int num_verts;         /* body-model vertices (SMPL-X: 10475) */
+} mhmr_config;
+
+/* Per-call outputs: device buffers owned by the caller (torch tensors), sized for max_persons.
+ * Person order = torch.where order (b, y, x) (model.py:149,616).  Nullable: v2d, z. */
+typedef struct mhmr_outputs {
+  float* scores_map;   /* [B, res, res]    'scores' (after NMS in inference mode, model.py:145-157)      */
+  int32_t* count;      /* [1]              number of detected persons P                                   */
+  int32_t* det_idx;    /* [3, max_persons] image index b, row y, col x of each person                     */
+  float* det_score;    /* [max_persons]    person 'scores'                                                */
+  float* offset;       /* [max_persons, 2] mlp_offset output (model.py:258)                               */
+  float* loc;          /* [max_persons, 2] 'loc' (model.py:272-275)                                       */
+  float* dist_pp;      /* [max_persons]    'dist_postprocessed' (raw pred_cam[:,0])                       */
+  float* dist;         /* [max_persons]    'dist' (model.py:189-203)                                      */
+  float* rotmat;       /* [max_persons, 53, 3, 3]                                                         */
+  float* rotvec;       /* [max_persons, 53, 3]                                                            */
+  float* shape;        /* [max_persons, num_betas]                                                        */
+  float* expression;   /* [max_persons, 10]                                                               */
+  float* transl;       /* [max_persons, 3]                                                                */
+  float* transl_pelvis;/* [max_persons, 3]                                                                */
+  float* v3d;          /* [max_persons, V, 3]                                                             */
+  float* v2d;          /* [max_persons, V, 2]   nullable (not part of the inference person dict)          */
+  float* j3d;          /* [max_persons, 127, 3]                                                           */
+  float* j2d;          /* [max_persons, 127, 2]                                                           */
+  float* z;            /* [B, N, D] backbone features (blocks/dinov2.py:25), nullable (stage parity)      */
+} mhmr_outputs;
+
+/* Replaces `Model(**ckpt_args)` (reference demo.py:98-100, model.py:33-131). */
+int mhmr_create(const mhmr_config* cfg, mhmr_engine** out);
+int mhmr_destroy(mhmr_engine* h);
+
+/* Replaces `model.load_state_dict(ckpt['model_state_dict'], strict=False)` (demo.py:103): one call per
+ * fp32 tensor, `key` = the reference's state_dict key.  `data` may be a host or a
+ * device pointer; the engine keeps its own device copy.  Extra keys the C-ABI expects:
+ *   backbone.encoder.pos_embed  must already be interpolated to the working grid: [1, 1+N, D]
+ *   camera.freq_bands           [16] = torch.linspace(1, 32, 16)   (blocks/camera_embed.py:46)
+ *   smplx.{v_template,shapedirs,expr_dirs,posedirs,J_regressor,lbs_weights,lmk_bary_coords}
+ *                               the buffers smplx.create() registers (blocks/smpl_layer.py:38). */
+int mhmr_set_weight(mhmr_engine* h, const char* key, const float* data, int64_t numel);
+/* Integer body-model tables: smplx.parents [55], smplx.extra_joints_idxs [21],
+ * smplx.lmk_tri [51*3] (= faces[lmk_faces_idx]). */
+int mhmr_set_table_i32(mhmr_engine* h, const char* key, const int32_t* data, int64_t numel);
+/* Repack (fp16 K-major weight tiles, fused tables, folded joint regressor), allocate workspaces, build
+ * TMA descriptors.  Fails if a required key is missing. */
+int mhmr_finalize(mhmr_engine* h);
+
+/* One forward of `Model.forward(x, idx, det_thresh, nms_kernel_size, K, is_training)` (model.py:205-349):
+ * x [B,3,S,S] fp32 NCHW and K [B,3,3] fp32 are DEVICE pointers.  forced_idx (nullable) is a device
+ * int64 [4, forced_P] tensor (b, y, x, c) = the reference's `idx=` argument (training-style path,
+ * model.py:150-151: no NMS/threshold).  Asynchronous on `stream`; no host synchronisation. */
+int mhmr_forward(mhmr_engine* h, const float* x, const float* K, int B, float det_thresh,
+                 int nms_kernel_size, const int64_t* forced_idx, int forced_P, const mhmr_outputs* out,
+                 void* stream);
+/* Waits for the forward enqueued last on `stream` and returns the person count; MHMR_ERR_CAPACITY if it
+ * exceeded max_persons (outputs are then incomplete — never silently truncated). */
+int mhmr_sync_count(mhmr_engine* h, void* stream, int* num_persons);
+
+/* Stage-level entry: backbone only (blocks/dinov2.py:16-26): x [B,3,S,S] -> z [B,N,D] fp32. */
+int mhmr_vit_forward(mhmr_engine* h, const float* x, int B, float* z, void* stream);
+/* Stage-level entry: SMPL-X layer only (blocks/smpl_layer.py:47-155) for P persons (device pointers):
+ * rotvec [P,53,3], shape [P,nb], expression [P,10], loc [P,2], dist [P], K_det [P,3,3]. */
+int mhmr_smplx_forward(mhmr_engine* h, int P, const float* rotvec, const float* shape,
+                       const float* expression, const float* loc, const float* dist, const float* K_det,
+                       float* v3d, float* v2d, float* j3d, float* j2d, float* transl, float* transl_pelvis,
+                       void* stream);
+/* Kernel launches enqueued by the last mhmr_forward (bench.py's `gpu_launches`). */
+int mhmr_last_launch_count(mhmr_engine* h);
+
 #ifdef __cplusplus
 }
 #endif

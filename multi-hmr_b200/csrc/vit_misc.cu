@@ -1,0 +1,190 @@
+// Memory-bound helpers of the ViT backbone: patch gathering (im2col for the 14x14/14 conv), LayerNorm
+// with fp16 / fp32 outputs, cls-token row initialisation, fp32->fp16 weight repacking.
+#include "kernels.cuh"
+
+namespace mhmr {
+
+namespace {
+
+// x [B,3,S,S] fp32 -> A [B*N, ldA] fp16, column k = c*196 + py*14 + px (Conv2d weight flattening order,
+// dinov2 PatchEmbed.proj reached from reference blocks/dinov2.py:25).  Columns >= 588 are never written
+// (they are out of the tensor-map bounds and read as zero by TMA).
+__global__ void im2col_patch14_kernel(const float* __restrict__ x, __half* __restrict__ A, int B, int S,
+                                      int ldA) {
+  const int hw = S / 14;
+  const int m = blockIdx.x;  // patch row index b*N + py_*hw + px_
+  const int N = hw * hw;
+  const int b = m / N, n = m - b * N;
+  const int gy = n / hw, gx = n - gy * hw;
+  const float* src = x + static_cast<int64_t>(b) * 3 * S * S;
+  __half* dst = A + static_cast<int64_t>(m) * ldA;
+  for (int k = threadIdx.x; k < 588; k += blockDim.x) {
+    const int c = k / 196, r = k - c * 196;
+    const int py = r / 14, px = r - py * 14;
+    dst[k] = __float2half_rn(src[(static_cast<int64_t>(c) * S + gy * 14 + py) * S + gx * 14 + px]);
+  }
+}
+
+// X[b*T + 0, :] = cls_pos (cls_token + pos_embed[0]) for every image.
+__global__ void cls_row_kernel(float* __restrict__ X, const float* __restrict__ cls_pos, int T, int D) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) X[static_cast<int64_t>(b) * T * D + i] = cls_pos[i];
+}
+
+// One warp per row.  Two-pass statistics in registers (mean, then centred sum of squares) in fp32.
+// Row remap (for the final norm, which drops the cls token): input row r = g*rows_in + t is skipped when
+// t < skip, else written to output row g*(rows_in - skip) + (t - skip).
+template <int VEC>  // D == 128 * VEC  (VEC float4 per lane)
+__global__ void layernorm_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __half* __restrict__ out16, int64_t ld16,
+                                 float* __restrict__ out32, int64_t ld32, int M, int D, float eps,
+                                 int rows_in, int skip) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  int64_t orow = row;
+  if (rows_in > 0) {
+    const int g = row / rows_in, t = row - g * rows_in;
+    if (t < skip) return;
+    orow = static_cast<int64_t>(g) * (rows_in - skip) + (t - skip);
+  }
+  const float4* xr = reinterpret_cast<const float4*>(X + static_cast<int64_t>(row) * D);
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + bb.x;
+    y.y = (v[i].y - mean) * rstd * g.y + bb.y;
+    y.z = (v[i].z - mean) * rstd * g.z + bb.z;
+    y.w = (v[i].w - mean) * rstd * g.w + bb.w;
+    if (out32 != nullptr)
+      reinterpret_cast<float4*>(out32 + orow * ld32)[lane + 32 * i] = y;
+    if (out16 != nullptr) {
+      const __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(out16 + orow * ld16)[lane + 32 * i] = pk;
+    }
+  }
+}
+
+__global__ void f32_to_f16_2d_kernel(const float* __restrict__ src, int64_t lds, __half* __restrict__ dst,
+                                     int64_t ldd, int rows, int cols) {
+  const int64_t total = static_cast<int64_t>(rows) * cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    dst[r * ldd + c] = __float2half_rn(src[r * lds + c]);
+  }
+}
+
+}  // namespace
+
+int im2col_patch14(const float* x, __half* A, int B, int S, int ldA, cudaStream_t stream) {
+  MHMR_REQUIRE(S % 14 == 0 && ldA >= 588, "im2col: bad geometry");
+  const int N = (S / 14) * (S / 14);
+  im2col_patch14_kernel<<<B * N, 128, 0, stream>>>(x, A, B, S, ldA);
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+int cls_rows(float* X, const float* cls_pos, int B, int T, int D, cudaStream_t stream) {
+  cls_row_kernel<<<B, 256, 0, stream>>>(X, cls_pos, T, D);
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+int layernorm(const float* X, const float* gamma, const float* beta, __half* out16, int64_t ld16,
+              float* out32, int64_t ld32, int M, int D, float eps, int rows_in, int skip,
+              cudaStream_t stream) {
+  MHMR_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D must be a multiple of 128, <= 1024");
+  MHMR_REQUIRE(out16 != nullptr || out32 != nullptr, "layernorm: no output");
+  const int wpb = 8;
+  dim3 grid((M + wpb - 1) / wpb), block(wpb * 32);
+#define MHMR_LN_CASE(V)                                                                              \
+  case V:                                                                                            \
+    layernorm_kernel<V><<<grid, block, 0, stream>>>(X, gamma, beta, out16, ld16, out32, ld32, M, D, \
+                                                    eps, rows_in, skip);                            \
+    break;
+  switch (D / 128) {
+    MHMR_LN_CASE(1) MHMR_LN_CASE(2) MHMR_LN_CASE(3) MHMR_LN_CASE(4) MHMR_LN_CASE(5) MHMR_LN_CASE(6)
+    MHMR_LN_CASE(7) MHMR_LN_CASE(8)
+    default: break;
+  }
+#undef MHMR_LN_CASE
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+int f32_to_f16_2d(const float* src, int64_t lds, __half* dst, int64_t ldd, int rows, int cols,
+                  cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(rows) * cols;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  f32_to_f16_2d_kernel<<<blocks, 256, 0, stream>>>(src, lds, dst, ldd, rows, cols);
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+}  // namespace mhmr
+
+namespace mhmr {
+namespace {
+// dst[r, dcol + c] = src[r, scol + c] for c < cols; when `zero_fill`, the rest of the dst row is zeroed.
+__global__ void repack_f32_kernel(const float* __restrict__ src, int64_t lds, int scol, float* __restrict__ dst,
+                                  int64_t ldd, int dcol, int rows, int cols, int zero_fill) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  if (zero_fill) {
+    for (int c = threadIdx.x; c < ldd; c += blockDim.x) {
+      const int sc = c - dcol;
+      dst[r * ldd + c] = (sc >= 0 && sc < cols) ? src[r * lds + scol + sc] : 0.f;
+    }
+  } else {
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) dst[r * ldd + dcol + c] = src[r * lds + scol + c];
+  }
+}
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                               int64_t n, int64_t b_period) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = a[i] + b[i % b_period];
+}
+}  // namespace
+
+int repack_f32(const float* src, int64_t lds, int scol, float* dst, int64_t ldd, int dcol, int rows,
+               int cols, bool zero_fill, cudaStream_t stream) {
+  repack_f32_kernel<<<rows, 256, 0, stream>>>(src, lds, scol, dst, ldd, dcol, rows, cols, zero_fill ? 1 : 0);
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+// out[i] = a[i] + b[i % b_period]
+int add_vec(const float* a, const float* b, float* out, int64_t n, int64_t b_period, cudaStream_t stream) {
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 2048) blocks = 2048;
+  add_vec_kernel<<<blocks, 256, 0, stream>>>(a, b, out, n, b_period);
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+}  // namespace mhmr
