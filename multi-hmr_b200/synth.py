@@ -118,7 +118,14 @@ def make_state_dict(backbone: str = "dinov2_vitl14", img_size: int = 896, num_be
         ln(p + "2.norm", HPH_DIM)
         lin(p + "2.fn.net.0", HPH_DIM, HPH_DIM)
         lin(p + "2.fn.net.3", HPH_DIM, HPH_DIM)
-    lin(h + "decpose", 318, HPH_DIM, std=0.02)
+    # Trained-like conditioning of the 6D pose head: joints 24..52 start from the degenerate init
+    # [1,0,0,1,0,0] (model.py:444-450: two identical columns after utils/humans.py:20), so a trained decoder
+    # must add ~[0,0,0,-1,1,0] to produce a valid rotation.  Random weights without that offset make the
+    # Gram-Schmidt step arbitrarily ill-conditioned (SURVEY.md §7 "hard parts"), which would measure the
+    # conditioning of the fixture rather than the kernels.
+    lin(h + "decpose", 318, HPH_DIM, std=0.005)
+    pose_bias = sd[h + "decpose.bias"].view(53, 6)
+    pose_bias[24:] += torch.tensor([0.0, 0.0, 0.0, -1.0, 1.0, 0.0])
     lin(h + "decshape", num_betas, HPH_DIM, std=0.01)
     lin(h + "deccam", 3, HPH_DIM, std=0.005)
     lin(h + "decexpression", 10, HPH_DIM, std=0.01)
