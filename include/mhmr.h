@@ -139,6 +139,23 @@ int mhmr_smplx_forward(mhmr_engine* h, int P, const float* rotvec, const float* 
 /* Kernel launches enqueued by the last mhmr_forward (bench.py's `gpu_launches`). */
 int mhmr_last_launch_count(mhmr_engine* h);
 
+/* Live per-kernel-family timing with CUDA events on the launching stream (bench.py's `roofline`):
+ * while enabled, every launch of mhmr_forward is bracketed by an event pair; mhmr_get_profile waits for
+ * them, returns the summed device milliseconds and launch counts per category and resets the record. */
+#define MHMR_CAT_MISC 0        /* im2col, cls rows                          */
+#define MHMR_CAT_LAYERNORM 1
+#define MHMR_CAT_GEMM_QKV 2
+#define MHMR_CAT_ATTENTION 3
+#define MHMR_CAT_GEMM_PROJ 4
+#define MHMR_CAT_GEMM_FC1 5
+#define MHMR_CAT_GEMM_FC2 6
+#define MHMR_CAT_GEMM_OTHER 7  /* patch-embed, detection hidden, HPH to_kv */
+#define MHMR_CAT_HEAD 8        /* detection / HPH / post-processing kernels */
+#define MHMR_CAT_SMPLX 9       /* prep + vertex + joints kernels            */
+#define MHMR_NUM_CATEGORIES 10
+int mhmr_set_profiling(mhmr_engine* h, int enable);
+int mhmr_get_profile(mhmr_engine* h, float* ms_by_category, int* launches_by_category);
+
 #ifdef __cplusplus
 }
 #endif

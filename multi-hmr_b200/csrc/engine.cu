@@ -50,6 +50,19 @@ struct mhmr_engine {
   std::map<std::string, DevBuf> tables;    // int32 tables
   std::vector<void*> owned;                // everything cudaMalloc'ed (freed in destroy)
   int launches = 0;
+  bool profiling = false;
+  struct ProfEntry { int cat; cudaEvent_t a, b; };
+  std::vector<ProfEntry> prof;
+  std::vector<cudaEvent_t> event_pool;
+  size_t events_used = 0;
+  cudaEvent_t next_event() {
+    if (events_used == event_pool.size()) {
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      event_pool.push_back(ev);
+    }
+    return event_pool[events_used++];
+  }
 
   // packed weights
   __half* Wpatch = nullptr;   // [D, 592]
@@ -83,6 +96,7 @@ struct mhmr_engine {
     for (auto& kv : weights) cudaFree(kv.second.p);
     for (auto& kv : tables) cudaFree(kv.second.p);
     if (h_count) cudaFreeHost(h_count);
+    for (cudaEvent_t ev : event_pool) cudaEventDestroy(ev);
   }
 
   template <typename T>
@@ -342,13 +356,25 @@ int finalize_body(mhmr_engine* e, cudaStream_t st) {
   return MHMR_OK;
 }
 
-#define LAUNCH(expr)            \
-  do {                          \
-    TRY(expr);                  \
-    ++e->launches;              \
+struct ProfScope {
+  mhmr_engine* e; int cat; cudaStream_t st; cudaEvent_t a{};
+  ProfScope(mhmr_engine* e_, int cat_, cudaStream_t st_) : e(e_), cat(cat_), st(st_) {
+    if (e->profiling) { a = e->next_event(); cudaEventRecord(a, st); }
+  }
+  ~ProfScope() {
+    if (e->profiling) { cudaEvent_t b = e->next_event(); cudaEventRecord(b, st); e->prof.push_back({cat, a, b}); }
+  }
+};
+
+#define LAUNCH(cat, expr)               \
+  do {                                  \
+    ProfScope ps_(e, cat, st);          \
+    TRY(expr);                          \
+    ++e->launches;                      \
   } while (0)
 
-int run_plan(mhmr_engine* e, GemmPlan& plan, int M, cudaStream_t st) {
+int run_plan(mhmr_engine* e, int cat, GemmPlan& plan, int M, cudaStream_t st) {
+  ProfScope ps_(e, cat, st);
   GemmPlan p = plan;  // tensor maps were built for the maximum M; the kernel bounds rows by p.M
   p.M = M;
   const int tiles = ((M + 127) / 128) * ((p.N + p.bn - 1) / p.bn);
@@ -361,23 +387,23 @@ int run_plan(mhmr_engine* e, GemmPlan& plan, int M, cudaStream_t st) {
 
 int vit_forward(mhmr_engine* e, const float* x, int B, float* z_out, cudaStream_t st) {
   const int D = e->D, N = e->N, T = e->T, M = B * T;
-  LAUNCH(im2col_patch14(x, e->A16, B, e->cfg.img_size, 592, st));
-  LAUNCH(cls_rows(e->X, e->cls_pos, B, T, D, st));
-  TRY(run_plan(e, e->patch_plan, B * N, st));
+  LAUNCH(MHMR_CAT_MISC, im2col_patch14(x, e->A16, B, e->cfg.img_size, 592, st));
+  LAUNCH(MHMR_CAT_MISC, cls_rows(e->X, e->cls_pos, B, T, D, st));
+  TRY(run_plan(e, MHMR_CAT_GEMM_OTHER, e->patch_plan, B * N, st));
   for (int l = 0; l < e->depth; ++l) {
     VitLayer& L = e->vit[l];
-    LAUNCH(layernorm(e->X, L.ln1_g, L.ln1_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
-    TRY(run_plan(e, L.qkv, M, st));
-    LAUNCH(attention_forward(e->QKV16, 3 * D, e->O16, D, B, T, D, st));
-    TRY(run_plan(e, L.proj, M, st));
-    LAUNCH(layernorm(e->X, L.ln2_g, L.ln2_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
-    TRY(run_plan(e, L.fc1, M, st));
-    TRY(run_plan(e, L.fc2, M, st));
+    LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln1_g, L.ln1_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
+    TRY(run_plan(e, MHMR_CAT_GEMM_QKV, L.qkv, M, st));
+    LAUNCH(MHMR_CAT_ATTENTION, attention_forward(e->QKV16, 3 * D, e->O16, D, B, T, D, st));
+    TRY(run_plan(e, MHMR_CAT_GEMM_PROJ, L.proj, M, st));
+    LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln2_g, L.ln2_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
+    TRY(run_plan(e, MHMR_CAT_GEMM_FC1, L.fc1, M, st));
+    TRY(run_plan(e, MHMR_CAT_GEMM_FC2, L.fc2, M, st));
   }
   // final norm, cls dropped: fp32 features (head query side, optional user copy) + fp16 context columns
   const float* ng = e->w("backbone.encoder.norm.weight");
   const float* nb = e->w("backbone.encoder.norm.bias");
-  LAUNCH(layernorm(e->X, ng, nb, e->ctx16, e->Cp, e->z32, D, M, D, 1e-6f, T, 1, st));
+  LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, ng, nb, e->ctx16, e->Cp, e->z32, D, M, D, 1e-6f, T, 1, st));
   if (z_out != nullptr)
     MHMR_CUDA_CHECK(cudaMemcpyAsync(z_out, e->z32, static_cast<size_t>(B) * N * D * 4, cudaMemcpyDeviceToDevice, st));
   return MHMR_OK;
@@ -389,63 +415,66 @@ int head_forward(mhmr_engine* e, const float* K, int B, float det_thresh, int nm
   const int heads = e->cfg.xat_num_heads, inner = heads * 32, BN = B * N;
   int* det_b = o->det_idx; int* det_y = o->det_idx + Pm; int* det_x = o->det_idx + 2 * Pm;
   int* count = o->count;
-  LAUNCH(invert_K(K, e->Kinv, B, st));
-  LAUNCH(ctx_fourier(e->Kinv, e->w("camera.freq_bands"), e->ctx16, e->Cp, B, res, D, e->Cp - D, st));
+  LAUNCH(MHMR_CAT_HEAD, invert_K(K, e->Kinv, B, st));
+  LAUNCH(MHMR_CAT_HEAD, ctx_fourier(e->Kinv, e->w("camera.freq_bands"), e->ctx16, e->Cp, B, res, D, e->Cp - D, st));
   // detection (model.py:133-158)
-  TRY(run_plan(e, e->cls0_plan, BN, st));
-  LAUNCH(rowdot_sigmoid(e->H16, D, e->w("mlp_classif.2.weight"), e->w("mlp_classif.2.bias"), e->scores_raw, BN, D, st));
+  TRY(run_plan(e, MHMR_CAT_GEMM_OTHER, e->cls0_plan, BN, st));
+  LAUNCH(MHMR_CAT_HEAD, rowdot_sigmoid(e->H16, D, e->w("mlp_classif.2.weight"), e->w("mlp_classif.2.bias"), e->scores_raw, BN, D, st));
   if (forced_idx != nullptr) {
-    LAUNCH(forced_detections(e->scores_raw, o->scores_map, B, res, forced_idx, forced_P, det_b, det_y, det_x,
+    LAUNCH(MHMR_CAT_HEAD, forced_detections(e->scores_raw, o->scores_map, B, res, forced_idx, forced_P, det_b, det_y, det_x,
                          o->det_score, count, e->img_off, st));
   } else {
-    LAUNCH(nms_compact(e->scores_raw, o->scores_map, B, res, nms, det_thresh, Pm, det_b, det_y, det_x,
+    LAUNCH(MHMR_CAT_HEAD, nms_compact(e->scores_raw, o->scores_map, B, res, nms, det_thresh, Pm, det_b, det_y, det_x,
                        o->det_score, count, e->img_off, st));
   }
   MHMR_CUDA_CHECK(cudaMemcpyAsync(e->h_count, count, sizeof(int), cudaMemcpyDeviceToHost, st));
   // keys / values of both decoder layers for every token (to_kv, cross_attn_transformer.py:187)
-  TRY(run_plan(e, e->kv_plan, BN, st));
+  TRY(run_plan(e, MHMR_CAT_GEMM_OTHER, e->kv_plan, BN, st));
   const std::string h = "x_attention_head.";
-  LAUNCH(person_gather(e->z32, e->Kinv, e->w("camera.freq_bands"), e->w(h + "cross_queries_x"),
+  LAUNCH(MHMR_CAT_HEAD, person_gather(e->z32, e->Kinv, e->w("camera.freq_bands"), e->w(h + "cross_queries_x"),
                        e->w(h + "cross_queries_y"), e->w(h + "cross_values_x"), e->w(h + "cross_values_y"),
                        det_b, det_y, det_x, count, Pm, res, D, e->zc, e->query, e->vals, Cq, st));
   // offset head (model.py:258)
-  LAUNCH(skinny_linear(e->zc, D, count, Pm, D, e->w("mlp_offset.0.weight"), D, e->w("mlp_offset.0.bias"), D,
+  LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->zc, D, count, Pm, D, e->w("mlp_offset.0.weight"), D, e->w("mlp_offset.0.bias"), D,
                        nullptr, nullptr, 0.f, 1, nullptr, 0, e->offh, D, st));
-  LAUNCH(skinny_linear(e->offh, D, count, Pm, D, e->w("mlp_offset.2.weight"), D, e->w("mlp_offset.2.bias"), 2,
+  LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->offh, D, count, Pm, D, e->w("mlp_offset.2.weight"), D, e->w("mlp_offset.2.bias"), 2,
                        nullptr, nullptr, 0.f, 0, nullptr, 0, o->offset, 2, st));
   // learned value embeddings injected at the detected cells (model.py:514-517)
-  LAUNCH(skinny_linear(e->vals, Cq, count, Pm, e->C, e->Wkv32, Cq, nullptr, e->nkv, nullptr, nullptr, 0.f, 0,
+  LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->vals, Cq, count, Pm, e->C, e->Wkv32, Cq, nullptr, e->nkv, nullptr, nullptr, 0.f, 0,
                        nullptr, 0, e->dKV, e->nkv, st));
-  LAUNCH(kv_add_rows(e->KV32, e->nkv, e->dKV, e->nkv, det_b, det_y, det_x, count, Pm, res, st));
+  LAUNCH(MHMR_CAT_HEAD, kv_add_rows(e->KV32, e->nkv, e->dKV, e->nkv, det_b, det_y, det_x, count, Pm, res, st));
   // token embedding (cross_attn_transformer.py:352-357)
-  LAUNCH(skinny_linear(e->query, Cq, count, Pm, e->C, e->Wte_q, Cq, e->te_const, kHphDim, nullptr, nullptr, 0.f,
+  LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->query, Cq, count, Pm, e->C, e->Wte_q, Cq, e->te_const, kHphDim, nullptr, nullptr, 0.f,
                        0, nullptr, 0, e->xa, kHphDim, st));
   for (int l = 0; l < e->cfg.xat_depth; ++l) {
     HphLayer& L = e->hph[l];
-    LAUNCH(skinny_linear(e->xa, kHphDim, count, Pm, kHphDim, L.Wqkv, kHphDim, nullptr, 3 * inner, L.ln0_g, L.ln0_b,
+    LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->xa, kHphDim, count, Pm, kHphDim, L.Wqkv, kHphDim, nullptr, 3 * inner, L.ln0_g, L.ln0_b,
                          1e-5f, 0, nullptr, 0, e->qkvp, 3 * inner, st));
-    LAUNCH(hph_self_attn(e->qkvp, 3 * inner, det_b, e->img_off, count, Pm, heads, e->att, inner, st));
-    LAUNCH(skinny_linear(e->att, inner, count, Pm, inner, L.Wsa_out, inner, L.bsa_out, kHphDim, nullptr, nullptr,
+    LAUNCH(MHMR_CAT_HEAD, hph_self_attn(e->qkvp, 3 * inner, det_b, e->img_off, count, Pm, heads, e->att, inner, st));
+    LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->att, inner, count, Pm, inner, L.Wsa_out, inner, L.bsa_out, kHphDim, nullptr, nullptr,
                          0.f, 0, e->xa, kHphDim, e->xa, kHphDim, st));
-    LAUNCH(skinny_linear(e->xa, kHphDim, count, Pm, kHphDim, L.Wq, kHphDim, nullptr, inner, L.ln1_g, L.ln1_b, 1e-5f,
+    LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->xa, kHphDim, count, Pm, kHphDim, L.Wq, kHphDim, nullptr, inner, L.ln1_g, L.ln1_b, 1e-5f,
                          0, nullptr, 0, e->qca, inner, st));
-    LAUNCH(hph_cross_attn(e->qca, inner, e->KV32, e->nkv, l * 2 * inner, l * 2 * inner + inner, det_b, count, Pm,
+    LAUNCH(MHMR_CAT_HEAD, hph_cross_attn(e->qca, inner, e->KV32, e->nkv, l * 2 * inner, l * 2 * inner + inner, det_b, count, Pm,
                           heads, N, e->att, inner, st));
-    LAUNCH(skinny_linear(e->att, inner, count, Pm, inner, L.Wca_out, inner, L.bca_out, kHphDim, nullptr, nullptr,
+    LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->att, inner, count, Pm, inner, L.Wca_out, inner, L.bca_out, kHphDim, nullptr, nullptr,
                          0.f, 0, e->xa, kHphDim, e->xa, kHphDim, st));
-    LAUNCH(skinny_linear(e->xa, kHphDim, count, Pm, kHphDim, L.Wff0, kHphDim, L.bff0, kHphDim, L.ln2_g, L.ln2_b,
+    LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->xa, kHphDim, count, Pm, kHphDim, L.Wff0, kHphDim, L.bff0, kHphDim, L.ln2_g, L.ln2_b,
                          1e-5f, 2, nullptr, 0, e->ffh, kHphDim, st));
-    LAUNCH(skinny_linear(e->ffh, kHphDim, count, Pm, kHphDim, L.Wff3, kHphDim, L.bff3, kHphDim, nullptr, nullptr,
+    LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->ffh, kHphDim, count, Pm, kHphDim, L.Wff3, kHphDim, L.bff3, kHphDim, nullptr, nullptr,
                          0.f, 0, e->xa, kHphDim, e->xa, kHphDim, st));
   }
-  LAUNCH(skinny_linear(e->xa, kHphDim, count, Pm, kHphDim, e->Wdec, kHphDim, e->bdec, e->ndec, nullptr, nullptr, 0.f,
+  LAUNCH(MHMR_CAT_HEAD, skinny_linear(e->xa, kHphDim, count, Pm, kHphDim, e->Wdec, kHphDim, e->bdec, e->ndec, nullptr, nullptr, 0.f,
                        0, nullptr, 0, e->dec, e->ndec, st));
   const float focal_norm = static_cast<float>(e->cfg.img_size / (2.0 * tan(30.0 * 3.14159265358979323846 / 180.0)));
-  LAUNCH(person_post(e->dec, e->ndec, nb, o->offset, K, e->Kinv, det_b, det_y, det_x, count, Pm, focal_norm,
+  LAUNCH(MHMR_CAT_HEAD, person_post(e->dec, e->ndec, nb, o->offset, K, e->Kinv, det_b, det_y, det_x, count, Pm, focal_norm,
                      o->rotmat, o->rotvec, o->shape, o->expression, o->dist_pp, o->dist, o->loc, o->transl,
                      e->K_det, st));
-  TRY(smplx_forward(e->bm, o->rotvec, o->shape, o->expression, o->transl, e->K_det, count, Pm, e->sx, o->v3d,
-                    o->v2d, o->j3d, o->j2d, o->transl_pelvis, st));
+  {
+    ProfScope ps_(e, MHMR_CAT_SMPLX, st);
+    TRY(smplx_forward(e->bm, o->rotvec, o->shape, o->expression, o->transl, e->K_det, count, Pm, e->sx, o->v3d,
+                      o->v2d, o->j3d, o->j2d, o->transl_pelvis, st));
+  }
   e->launches += 3;
   return MHMR_OK;
 }
@@ -577,5 +606,28 @@ int mhmr_smplx_forward(mhmr_engine* h, int P, const float* rotvec, const float* 
 }
 
 int mhmr_last_launch_count(mhmr_engine* h) { return h != nullptr ? h->launches : 0; }
+
+int mhmr_set_profiling(mhmr_engine* h, int enable) {
+  MHMR_REQUIRE(h != nullptr, "null engine");
+  h->profiling = enable != 0;
+  h->prof.clear();
+  h->events_used = 0;
+  return MHMR_OK;
+}
+
+int mhmr_get_profile(mhmr_engine* h, float* ms_by_category, int* launches_by_category) {
+  MHMR_REQUIRE(h != nullptr && ms_by_category != nullptr && launches_by_category != nullptr, "null argument");
+  for (int c = 0; c < MHMR_NUM_CATEGORIES; ++c) { ms_by_category[c] = 0.f; launches_by_category[c] = 0; }
+  for (const auto& p : h->prof) {
+    MHMR_CUDA_CHECK(cudaEventSynchronize(p.b));
+    float ms = 0.f;
+    MHMR_CUDA_CHECK(cudaEventElapsedTime(&ms, p.a, p.b));
+    ms_by_category[p.cat] += ms;
+    launches_by_category[p.cat] += 1;
+  }
+  h->prof.clear();
+  h->events_used = 0;
+  return MHMR_OK;
+}
 
 }  // extern "C"

@@ -239,6 +239,7 @@ class Model:
               "mhmr_forward")
         n = c_int(0)
         check(self._lib.mhmr_sync_count(self._handle, stream, ctypes.byref(n)), "mhmr_sync_count")
+        self.last_outputs = t
         return t, int(n.value)
 
     def forward(self, x, idx=None, det_thresh=0.3, nms_kernel_size=3, K=None, is_training=False, *args, **kwargs):
@@ -301,3 +302,17 @@ class Model:
 
     def last_launch_count(self) -> int:
         return int(self._lib.mhmr_last_launch_count(self._handle))
+
+    PROFILE_CATEGORIES = ("misc", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2",
+                          "gemm_other", "head", "smplx")
+
+    def set_profiling(self, enable: bool):
+        self.finalize()
+        check(self._lib.mhmr_set_profiling(self._handle, c_int(1 if enable else 0)), "mhmr_set_profiling")
+
+    def get_profile(self) -> dict:
+        """{category: (device ms summed over launches, launches)} since profiling was enabled / last read."""
+        n = len(self.PROFILE_CATEGORIES)
+        ms, cnt = (ctypes.c_float * n)(), (ctypes.c_int * n)()
+        check(self._lib.mhmr_get_profile(self._handle, ms, cnt), "mhmr_get_profile")
+        return {c: (float(ms[i]), int(cnt[i])) for i, c in enumerate(self.PROFILE_CATEGORIES)}
