@@ -30,6 +30,30 @@ constexpr uint32_t kColO = 192;
 constexpr int kTmemCols = 256;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 2^x for a pair on the FMA/ALU pipes: n = round(x) through the 1.5*2^23 magic constant, cubic minimax
+// of 2^f on [-0.5, 0.5], exponent inserted with one shift-add.  Inputs are clamped to >= -126.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float kMagic = 12582912.0f;
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 xf = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 nf = __fadd2_rn(xf, make_float2(-kMagic, -kMagic));
+  const float2 f = __ffma2_rn(nf, make_float2(-1.0f, -1.0f), x);
+  float2 pl = __ffma2_rn(make_float2(0.0551716648f, 0.0551716648f), f, make_float2(0.2426111251f, 0.2426111251f));
+  pl = __ffma2_rn(pl, f, make_float2(0.6932609677f, 0.6932609677f));
+  pl = __ffma2_rn(pl, f, make_float2(0.9999280572f, 0.9999280572f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(xf.x) << 23));
+  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(xf.y) << 23));
+  return r;
+}
+
+template <int kExpMode>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
                 int T, int D, float scale_log2) {
@@ -163,18 +187,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);
 
-      const int valid = T - j * kBlockKV;  // keys of this tile that exist (>= 128 except last tile)
-      float mx = -INFINITY;
+      if (j == n_kv - 1) {  // only the last tile can hold keys beyond T (or rows of the next image)
+        const int valid = T - j * kBlockKV;
+        if (valid < kBlockKV) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(s[c][i]);
-          if (valid < kBlockKV && (c * 32 + i) >= valid) v = -INFINITY;
-          s[c][i] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
         }
       }
+      // row max: four independent chains (3-input max), then combine
+      float mxa[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
+#pragma unroll
+        for (int i = 2; i < 32; i += 2)
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+        mxa[c] = m0;
+      }
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
       const float m_new = fmaxf(m_used, mx * scale_log2);
       bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile (m_used = -inf)
       float alpha = 1.0f;
@@ -182,18 +215,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         alpha = exp2f(m_used - m_new);  // 0 on the first tile
         m_used = m_new;
       }
-      float sum = 0.0f;
+      float sum;
       uint32_t p[2][32];
+      const float2 sc2 = make_float2(scale_log2, scale_log2);
+      const float2 nm2 = make_float2(-m_used, -m_used);
+      {
+        // exponentials: MUFU.EX2 (16/clk/SM) is the binding pipe for head dim 64, so in kExpMode 1 three
+        // pairs out of eight are evaluated on the FMA pipes instead (Cody-Waite + cubic, rel. err 7.5e-5,
+        // far below the fp16 rounding of P).  Packed f32x2 FMA/ADD, two independent accumulator pairs.
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float e0 = exp2f(fmaf(__uint_as_float(s[c][i]), scale_log2, -m_used));
-          const float e1 = exp2f(fmaf(__uint_as_float(s[c][i + 1]), scale_log2, -m_used));
-          sum += e0 + e1;
-          const __half2 h = __floats2half2_rn(e0, e1);
-          p[c >> 1][(c & 1) * 16 + i / 2] = *reinterpret_cast<const uint32_t*>(&h);
+          for (int i = 0; i < 32; i += 4) {
+            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+            const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
+            const bool poly0 = (kExpMode == 1) && (pair == 0 || pair == 4);
+            const bool poly1 = (kExpMode == 1) && (pair + 1 == 3);
+            const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
+            const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
+            acc0 = __fadd2_rn(acc0, e0);
+            acc1 = __fadd2_rn(acc1, e1);
+            const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
+            p[c >> 1][(c & 1) * 16 + i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
+            p[c >> 1][(c & 1) * 16 + i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+          }
         }
+        sum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
       }
       l = l * alpha + sum;
 
@@ -256,7 +305,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   }
 }
 
+int g_attn_exp_mode = 0;
+
 }  // namespace
+
+void attention_set_exp_mode(int mode) { g_attn_exp_mode = mode; }
 
 // qkv: [B*T, 3*D] fp16 (row pitch ld_qkv), q|k|v column blocks, head h = columns h*64..h*64+63 of each.
 // out: [B*T, D] fp16 (row pitch ldo).
@@ -271,13 +324,18 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   if (rc != MHMR_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kAttnSmem));
     attr_set = true;
   }
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   dim3 grid((T + kBlockQ - 1) / kBlockQ, D / kHeadDim, B);
-  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2);
+  if (g_attn_exp_mode == 1)
+    attn_fwd_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2);
+  else
+    attn_fwd_kernel<0><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2);
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }

@@ -21,12 +21,17 @@ def _ref(qkv, B, T, D):
     (2, 4097, 1024, 1.0),   # 896 / 14 grid + cls (ViT-L)
     (1, 1000, 128, 4.0),    # peaky softmax: exercises the lazy-rescale path
 ])
-def test_attention_matches_fp32(cuda_device, B, T, D, scale):
+@pytest.mark.parametrize("exp_mode", [0, 1])
+def test_attention_matches_fp32(cuda_device, B, T, D, scale, exp_mode):
     from multihmr_b200 import ops
 
     g = torch.Generator(device="cpu").manual_seed(B * 1000 + T + D)
     qkv = (torch.randn(B * T, 3 * D, generator=g) * scale).to(cuda_device).half()
-    out = ops.attention(qkv, B, T, D)
+    ops.set_attention_exp_mode(exp_mode)
+    try:
+        out = ops.attention(qkv, B, T, D)
+    finally:
+        ops.set_attention_exp_mode(0)
     ref = _ref(qkv, B, T, D)
     err = (out.float() - ref).abs().max().item()
     # P is rounded to fp16 (2^-11 relative) before the PV product and the output is fp16
