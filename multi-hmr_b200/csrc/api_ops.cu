@@ -36,7 +36,7 @@ int mhmr_op_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, i
 }
 
 int mhmr_set_attention_exp_mode(int mode) {
-  MHMR_REQUIRE(mode == 0 || mode == 1, "attention exp mode must be 0 (MUFU) or 1 (MUFU + polynomial)");
+  MHMR_REQUIRE(mode >= 0 && mode <= 3, "attention mode: bit0 = polynomial exp offload, bit1 = 2 softmax threads per row");
   attention_set_exp_mode(mode);
   return MHMR_OK;
 }

@@ -20,9 +20,8 @@ constexpr int kHeadDim = 64;
 constexpr int kBlockQ = 128;
 constexpr int kBlockKV = 128;
 constexpr int kStagesKV = 2;
-constexpr int kAttnThreads = 192;
 constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: Q, K or V tile
-constexpr int kAttnSmem = kTileBytes * (1 + 2 * kStagesKV) + 256 + 1024;
+constexpr int kAttnSmem = kTileBytes * (1 + 2 * kStagesKV) + 4096 + 1024;  // tiles + barriers/exchange + align
 
 constexpr uint32_t kColS = 0;
 constexpr uint32_t kColP = 128;
@@ -53,10 +52,22 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   return r;
 }
 
-template <int kExpMode>
-__global__ void __launch_bounds__(kAttnThreads, 2)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// kSplit = softmax threads per query row (1: 4 softmax warps, 2: 8 softmax warps, each thread owning half
+// of the key columns of its row; the two threads of a row exchange their partial row max through smem).
+template <int kExpMode, int kSplit>
+__global__ void __launch_bounds__(64 + 128 * kSplit, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
                 int T, int D, float scale_log2) {
+  constexpr int kColsPerThread = kBlockKV / kSplit;  // S columns per softmax thread
+  constexpr int kChunks = kColsPerThread / 32;
+  constexpr int kOCols = kHeadDim / kSplit;          // O columns per softmax thread
+  constexpr int kOChunks = kOCols / 32;
+  constexpr int kSoftmaxWarps = 4 * kSplit;
+
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -73,6 +84,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   uint64_t* p_full = s_empty + 1;          // softmax -> MMA : P_j in TMEM (and O rescaled)
   uint64_t* pv_done = p_full + 1;          // MMA -> softmax : O += P_j V_j complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [2][2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,8 +103,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         mbar_init(&kv_empty[s], 1);
       }
       mbar_init(s_full, 1);
-      mbar_init(s_empty, 4);
-      mbar_init(p_full, 4);
+      mbar_init(s_empty, kSoftmaxWarps);
+      mbar_init(p_full, kSoftmaxWarps);
       mbar_init(pv_done, 1);
       fence_barrier_init();
     }
@@ -166,22 +178,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
     }
   } else {
     // ------------------------------ Softmax warps ------------------------------
-    const int sub = warp & 3;  // TMEM sub-partition
+    const int sub = warp & 3;             // TMEM sub-partition (lane quarter) of this warp
+    const int half = (warp - 2) >> 2;     // which column half of the row (always 0 when kSplit == 1)
     const int row = sub * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(sub * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_base + kColS;
-    const uint32_t t_p = tmem_base + lane_base + kColP;
-    const uint32_t t_o = tmem_base + lane_base + kColO;
+    const uint32_t t_s = tmem_base + lane_base + kColS + half * kColsPerThread;
+    const uint32_t t_p = tmem_base + lane_base + kColP + half * (kColsPerThread / 2);
+    const uint32_t t_o = tmem_base + lane_base + kColO + half * kOCols;
+    const int col_base = half * kColsPerThread;
 
     float m_used = -INFINITY;  // running max (log2 domain) actually used as the exponent offset
-    float l = 0.0f;
+    float l = 0.0f;            // (partial, per thread) running row sum
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1u);
       tc_fence_after();
-      uint32_t s[4][32];
+      uint32_t s[kChunks][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
+      for (int c = 0; c < kChunks; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -191,78 +205,77 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         const int valid = T - j * kBlockKV;
         if (valid < kBlockKV) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < kChunks; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+              if (col_base + c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
         }
       }
-      // row max: four independent chains (3-input max), then combine
-      float mxa[4];
+      // row max: independent chains (3-input max), then combine
+      float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < kChunks; ++c) {
         float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
 #pragma unroll
         for (int i = 2; i < 32; i += 2)
           m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
-        mxa[c] = m0;
+        mx = fmaxf(mx, m0);
       }
-      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+      if constexpr (kSplit == 2) {
+        float* x = xch + (j & 1) * 256;
+        x[half * 128 + row] = mx;
+        named_bar_sync(1 + sub, 64);
+        mx = fmaxf(mx, x[(1 - half) * 128 + row]);
+      }
       const float m_new = fmaxf(m_used, mx * scale_log2);
-      bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile (m_used = -inf)
+      const bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile (m_used = -inf)
       float alpha = 1.0f;
       if (rescale) {
         alpha = exp2f(m_used - m_new);  // 0 on the first tile
         m_used = m_new;
       }
-      float sum;
-      uint32_t p[2][32];
-      const float2 sc2 = make_float2(scale_log2, scale_log2);
-      const float2 nm2 = make_float2(-m_used, -m_used);
-      {
-        // exponentials: MUFU.EX2 (16/clk/SM) is the binding pipe for head dim 64, so in kExpMode 1 three
-        // pairs out of eight are evaluated on the FMA pipes instead (Cody-Waite + cubic, rel. err 7.5e-5,
-        // far below the fp16 rounding of P).  Packed f32x2 FMA/ADD, two independent accumulator pairs.
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
-            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
-            const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
-            const bool poly0 = (kExpMode == 1) && (pair == 0 || pair == 4);
-            const bool poly1 = (kExpMode == 1) && (pair + 1 == 3);
-            const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
-            const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
-            acc0 = __fadd2_rn(acc0, e0);
-            acc1 = __fadd2_rn(acc1, e1);
-            const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
-            p[c >> 1][(c & 1) * 16 + i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
-            p[c >> 1][(c & 1) * 16 + i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-          }
-        }
-        sum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
-      }
-      l = l * alpha + sum;
-
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1u);  // P buffer free, O stable
         tc_fence_after();
-        if (__any_sync(0xffffffffu, rescale)) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32(t_o + c * 32, o);
+        if (__any_sync(0xffffffffu, rescale)) {  // rare after the first tiles: small chunks, few registers
+#pragma unroll 1
+          for (int c = 0; c < kOCols / 8; ++c) {
+            uint32_t o[8];
+            tmem_ld_32x8(t_o + c * 8, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(t_o + c * 32, o);
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x8(t_o + c * 8, o);
           }
         }
       }
-      tmem_st_32x32(t_p, p[0]);
-      tmem_st_32x32(t_p + 32, p[1]);
+      // exponentials: MUFU.EX2 (16/clk/SM) is the binding pipe for head dim 64, so in kExpMode 1 three
+      // pairs out of eight are evaluated on the FMA pipes instead (Cody-Waite + cubic, rel. err 7.5e-5,
+      // far below the fp16 rounding of P).  Packed f32x2 FMA/ADD, two independent accumulator pairs.
+      const float2 sc2 = make_float2(scale_log2, scale_log2);
+      const float2 nm2 = make_float2(-m_used, -m_used);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t p[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+          const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+          const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
+          const bool poly0 = (kExpMode == 1) && (pair == 0 || pair == 4);
+          const bool poly1 = (kExpMode == 1) && (pair + 1 == 3);
+          const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
+          const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
+          acc0 = __fadd2_rn(acc0, e0);
+          acc1 = __fadd2_rn(acc1, e1);
+          const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
+          p[i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
+          p[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        }
+        tmem_st_32x16(t_p + c * 16, p);
+      }
+      l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -272,11 +285,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
     // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
     mbar_wait(pv_done, (n_kv - 1) & 1u);
     tc_fence_after();
+    if constexpr (kSplit == 2) {
+      float* x = xch + (n_kv & 1) * 256;
+      x[half * 128 + row] = l;
+      named_bar_sync(1 + sub, 64);
+      l += x[(1 - half) * 128 + row];
+    }
     const float inv_l = 1.0f / l;
     const int q = q0 + row;
-    __half* dst = out + static_cast<int64_t>(row0 + q) * ldo + head * kHeadDim;
+    __half* dst = out + static_cast<int64_t>(row0 + q) * ldo + head * kHeadDim + half * kOCols;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < kOChunks; ++c) {
       uint32_t o[32];
       tmem_ld_32x32(t_o + c * 32, o);
       tmem_ld_wait();
@@ -324,18 +343,20 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   if (rc != MHMR_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     attr_set = true;
   }
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   dim3 grid((T + kBlockQ - 1) / kBlockQ, D / kHeadDim, B);
-  if (g_attn_exp_mode == 1)
-    attn_fwd_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2);
-  else
-    attn_fwd_kernel<0><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2);
+  switch (g_attn_exp_mode & 3) {
+    case 0: attn_fwd_kernel<0, 1><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
+    case 1: attn_fwd_kernel<1, 1><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
+    case 2: attn_fwd_kernel<0, 2><<<grid, 320, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
+    default: attn_fwd_kernel<1, 2><<<grid, 320, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
+  }
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }

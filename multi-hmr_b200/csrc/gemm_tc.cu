@@ -1,10 +1,11 @@
 // tcgen05 + TMA + TMEM persistent GEMM (see gemm_tc.cuh for the contract).
 //
-// CTA = 256 threads, one CTA per SM, persistent over output tiles (128 x BN):
-//   warp 0   : TMA producer   (one elected lane)   global -> 128B-swizzled smem ring
-//   warp 1   : MMA issuer     (one elected lane)   tcgen05.mma kind::f16, M=128, N=BN, K=16
-//   warp 2   : TMEM allocator (2 x BN fp32 columns: double-buffered accumulator)
-//   warps 4-7: epilogue       tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+// CTA = 384 threads, one CTA per SM, persistent over output tiles (128 x BN):
+//   warp 0    : TMA producer   (one elected lane)   global -> 128B-swizzled smem ring
+//   warp 1    : MMA issuer     (one elected lane)   tcgen05.mma kind::f16, M=128, N=BN, K=16
+//   warp 2    : TMEM allocator (2 x BN fp32 columns: double-buffered accumulator)
+//   warps 4-11: epilogue       tcgen05.ld 32x32b -> registers -> smem transpose -> fused epilogue with
+//                              coalesced 128-bit global accesses (two warps per TMEM sub-partition)
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue), so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include "gemm_tc.cuh"
@@ -16,81 +17,112 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + 32 * kEpiWarps;  // TMA, MMA, TMEM-alloc, spare + epilogue warps
+constexpr int kScratchStride = 36;               // floats per scratch row (32 + 4: conflict-free float4)
+constexpr int kScratchBytes = 32 * kScratchStride * 4;
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 3 : 5;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual align
-  static constexpr int kTmemCols = 2 * BN;                                    // 256 or 512
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kEpiWarps * kScratchBytes + kBarBytes + 1024;  // +1024: manual align
+  static constexpr int kTmemCols = 2 * BN;                                  // 256 or 512
 };
 
-// One thread owns one output row; `r` holds 32 consecutive fp32 accumulator columns [n0, n0+32).
+// The accumulator chunk (32 rows x 32 columns, one row per thread after tcgen05.ld) is transposed through
+// a per-warp smem scratch so that global memory is accessed with lanes along the contiguous dimension:
+//   fp32 outputs: 8 lanes x float4 cover one 128-byte row segment, 4 rows per warp instruction;
+//   fp16 outputs: 4 lanes x (8 halves) cover one 64-byte row segment, 8 rows per warp instruction.
 template <int EPI>
-__device__ __forceinline__ void epilogue_store_chunk(const uint32_t (&r)[32], const GemmEpi& ep,
-                                                     int N, int64_t out_row, int row_in_group,
-                                                     int n0) {
-  if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_RELU_F16) {
-    __half* out = reinterpret_cast<__half*>(ep.out) + out_row * ep.ldo + n0;
-    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* scratch, const GemmEpi& ep,
+                                               int M, int N, int m_base, int n0, int lane) {
+  constexpr bool kF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_RELU_F16);
+  // (a) rows -> scratch
+  float* my = scratch + lane * kScratchStride;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float x[8];
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(my + q * 4) =
+        make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                    __uint_as_float(r[q * 4 + 3]));
+  __syncwarp();
+  if constexpr (kF16) {
+    const int cg = lane & 3, rs = lane >> 2;  // 8 columns per lane, 8 rows per instruction
+    const int n = n0 + cg * 8;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4 b = __ldg(b4 + q * 2 + h);
-        x[h * 4 + 0] = __uint_as_float(r[q * 8 + h * 4 + 0]) + b.x;
-        x[h * 4 + 1] = __uint_as_float(r[q * 8 + h * 4 + 1]) + b.y;
-        x[h * 4 + 2] = __uint_as_float(r[q * 8 + h * 4 + 2]) + b.z;
-        x[h * 4 + 3] = __uint_as_float(r[q * 8 + h * 4 + 3]) + b.w;
-      }
+    for (int k = 0; k < 4; ++k) {
+      const int rl = k * 8 + rs;
+      const int m = m_base + rl;
+      const float4 v0 = *reinterpret_cast<const float4*>(scratch + rl * kScratchStride + cg * 8);
+      const float4 v1 = *reinterpret_cast<const float4*>(scratch + rl * kScratchStride + cg * 8 + 4);
+      float x[8] = {v0.x + b0.x, v0.y + b0.y, v0.z + b0.z, v0.w + b0.w,
+                    v1.x + b1.x, v1.y + b1.y, v1.z + b1.z, v1.w + b1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if constexpr (EPI == EPI_BIAS_GELU_F16) x[i] = gelu_erf(x[i]);
         if constexpr (EPI == EPI_BIAS_RELU_F16) x[i] = fmaxf(x[i], 0.0f);
       }
-      const __half2 h0 = __floats2half2_rn(x[0], x[1]);
-      const __half2 h1 = __floats2half2_rn(x[2], x[3]);
-      const __half2 h2 = __floats2half2_rn(x[4], x[5]);
-      const __half2 h3 = __floats2half2_rn(x[6], x[7]);
+      const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
+      const __half2 h2 = __floats2half2_rn(x[4], x[5]), h3 = __floats2half2_rn(x[6], x[7]);
       uint4 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&h0);
       pk.y = *reinterpret_cast<const uint32_t*>(&h1);
       pk.z = *reinterpret_cast<const uint32_t*>(&h2);
       pk.w = *reinterpret_cast<const uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>(out + q * 8) = pk;
+      if (m < M)
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out) + static_cast<int64_t>(m) * ep.ldo + n) = pk;
     }
   } else {
-    float* out = reinterpret_cast<float*>(ep.out) + out_row * ep.ldo + n0;
+    const int cg = lane & 7, rs = lane >> 3;  // 4 columns per lane, 4 rows per instruction
+    const int n = n0 + cg * 4;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if constexpr (EPI == EPI_LS_RESID_F32) {
+      b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+      g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
+    } else if constexpr (EPI == EPI_BIAS_F32) {
+      if (ep.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+    }
+    float* outp[8];
+    float4 xres[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 a = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
-                             __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
-      if constexpr (EPI == EPI_LS_RESID_F32) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + q);
-        const float4 g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n0) + q);
-        const float4 x = *reinterpret_cast<const float4*>(out + q * 4);
-        a.x = x.x + g.x * (a.x + b.x);
-        a.y = x.y + g.y * (a.y + b.y);
-        a.z = x.z + g.z * (a.z + b.z);
-        a.w = x.w + g.w * (a.w + b.w);
-      } else if constexpr (EPI == EPI_ROWADD_F32) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(
-                                   ep.rowadd + static_cast<int64_t>(row_in_group) * N + n0) + q);
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-      } else {  // EPI_BIAS_F32
-        if (ep.bias != nullptr) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + q);
-          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        }
+    for (int k = 0; k < 8; ++k) {
+      const int m = m_base + k * 4 + rs;
+      int64_t orow = m;
+      if constexpr (EPI == EPI_ROWADD_F32) {
+        const int grp = m / ep.rows_in, rin = m - grp * ep.rows_in;
+        orow = static_cast<int64_t>(grp) * ep.rows_out + ep.row_off + rin;
+        xres[k] = (m < M) ? __ldg(reinterpret_cast<const float4*>(ep.rowadd + static_cast<int64_t>(rin) * N + n))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      *reinterpret_cast<float4*>(out + q * 4) = a;
+      outp[k] = reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n;
+      if constexpr (EPI == EPI_LS_RESID_F32)
+        xres[k] = (m < M) ? *reinterpret_cast<const float4*>(outp[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int rl = k * 4 + rs;
+      const float4 v = *reinterpret_cast<const float4*>(scratch + rl * kScratchStride + cg * 4);
+      float4 a;
+      if constexpr (EPI == EPI_LS_RESID_F32) {
+        a.x = xres[k].x + g.x * (v.x + b.x);
+        a.y = xres[k].y + g.y * (v.y + b.y);
+        a.z = xres[k].z + g.z * (v.z + b.z);
+        a.w = xres[k].w + g.w * (v.w + b.w);
+      } else if constexpr (EPI == EPI_ROWADD_F32) {
+        a.x = v.x + xres[k].x; a.y = v.y + xres[k].y; a.z = v.z + xres[k].z; a.w = v.w + xres[k].w;
+      } else {
+        a.x = v.x + b.x; a.y = v.y + b.y; a.z = v.z + b.z; a.w = v.w + b.w;
+      }
+      if (m_base + rl < M) *reinterpret_cast<float4*>(outp[k]) = a;
     }
   }
+  __syncwarp();
 }
 
 template <int BN, int EPI>
@@ -103,7 +135,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  float* scratch_base = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + kEpiWarps * kScratchBytes);
   uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;       // [kStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kStages;   // [2]        MMA -> epilogue
@@ -129,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -188,7 +221,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ------------------------------ Epilogue -----------------------------------
-    const int ew = warp & 3;  // TMEM sub-partition of this warp: lanes [32*ew, 32*ew+32)
+    const int ew = warp & 3;             // TMEM sub-partition of this warp: lanes [32*ew, 32*ew+32)
+    const int par = (warp - 4) >> 2;     // two warps per sub-partition split the column chunks
+    float* scratch = scratch_base + (warp - 4) * (kScratchBytes / 4);
     uint32_t acc_iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_iter) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -196,26 +231,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aphase = (acc_iter >> 1) & 1u;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int m = m_blk * BM + ew * 32 + lane;
-      int64_t out_row = m;
-      int row_in_group = 0;
-      if (ep.rows_in > 0) {
-        const int g = m / ep.rows_in;
-        row_in_group = m - g * ep.rows_in;
-        out_row = static_cast<int64_t>(g) * ep.rows_out + ep.row_off + row_in_group;
-      }
+      const int m_base = m_blk * BM + ew * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+      constexpr int kChunksPerWarp = BN / 32 / (kEpiWarps / 4);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+        const int c = ci * (kEpiWarps / 4) + par;
         uint32_t r[32];
         tmem_ld_32x32(t_row + c * 32, r);
         tmem_ld_wait();
+        if (ci == kChunksPerWarp - 1) {  // accumulator fully read by this warp: hand it back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
         const int n0 = n_blk * BN + c * 32;
-        if (m < M && n0 < N) epilogue_store_chunk<EPI>(r, ep, N, out_row, row_in_group, n0);
+        if (n0 < N) epilogue_chunk<EPI>(r, scratch, ep, M, N, m_base, n0, lane);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
   }
 
