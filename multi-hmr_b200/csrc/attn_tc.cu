@@ -58,7 +58,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // kSplit = softmax threads per query row (1: 4 softmax warps, 2: 8 softmax warps, each thread owning half
 // of the key columns of its row; the two threads of a row exchange their partial row max through smem).
-template <int kExpMode, int kSplit>
+template <int kExpMode, int kSplit, int kPipe>
 __global__ void __launch_bounds__(64 + 128 * kSplit, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
                 int T, int D, float scale_log2) {
@@ -190,6 +190,113 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
     float m_used = -INFINITY;  // running max (log2 domain) actually used as the exponent offset
     float l = 0.0f;            // (partial, per thread) running row sum
 
+    if constexpr (kPipe == 1) {
+      // Software-pipelined variant (one thread per row): while the exponentials of tile j are being
+      // computed, the scores of tile j+1 are already streamed from TMEM into the registers freed chunk by
+      // chunk, so that the only non-MUFU phase left between two tiles is the row-max reduction.
+      static_assert(kSplit == 1, "pipelined softmax uses one thread per row");
+      uint32_t s[4][32];
+      auto tile_max = [&](int jt) -> float {
+        if (jt == n_kv - 1) {  // only the last tile can hold keys beyond T (or rows of the next image)
+          const int valid = T - jt * kBlockKV;
+          if (valid < kBlockKV) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
+          }
+        }
+        float mxa[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
+#pragma unroll
+          for (int i = 2; i < 32; i += 2)
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+          mxa[c] = m0;
+        }
+        return fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+      };
+      mbar_wait(s_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+      float mx = tile_max(0);
+
+      for (int j = 0; j < n_kv; ++j) {
+        const bool has_next = (j + 1) < n_kv;
+        const float m_new = fmaxf(m_used, mx * scale_log2);
+        const bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile
+        float alpha = 1.0f;
+        if (rescale) {
+          alpha = exp2f(m_used - m_new);  // 0 on the first tile
+          m_used = m_new;
+        }
+        if (j > 0) {
+          mbar_wait(pv_done, (j - 1) & 1u);  // P buffer free, O stable
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, rescale)) {
+#pragma unroll 1
+            for (int c = 0; c < kHeadDim / 8; ++c) {
+              uint32_t o[8];
+              tmem_ld_32x8(t_o + c * 8, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x8(t_o + c * 8, o);
+            }
+          }
+        }
+        const float2 sc2 = make_float2(scale_log2, scale_log2);
+        const float2 nm2 = make_float2(-m_used, -m_used);
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t p[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+            const int pair = (i >> 1) & 7;
+            const bool poly0 = (kExpMode == 1) && (pair == 0 || pair == 4);
+            const bool poly1 = (kExpMode == 1) && (pair + 1 == 3);
+            const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
+            const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
+            acc0 = __fadd2_rn(acc0, e0);
+            acc1 = __fadd2_rn(acc1, e1);
+            const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
+            p[i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
+            p[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+          }
+          tmem_st_32x16(t_p + c * 16, p);
+          if (has_next) {
+            if (c == 1) {  // S_{j+1} was issued when this thread released S_j, one tile ago
+              mbar_wait(s_full, (j + 1) & 1u);
+              tc_fence_after();
+            }
+            if (c >= 1) tmem_ld_32x32(t_s + (c - 1) * 32, s[c - 1]);  // registers of chunk c-1 are free
+          }
+        }
+        l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        if (has_next) {
+          tmem_ld_32x32(t_s + 3 * 32, s[3]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty);
+          mx = tile_max(j + 1);
+        }
+      }
+    } else {
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1u);
       tc_fence_after();
@@ -282,6 +389,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
       if (lane == 0) mbar_arrive(p_full);
     }
 
+    }
+
     // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
     mbar_wait(pv_done, (n_kv - 1) & 1u);
     tc_fence_after();
@@ -343,19 +452,23 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   if (rc != MHMR_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     attr_set = true;
   }
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   dim3 grid((T + kBlockQ - 1) / kBlockQ, D / kHeadDim, B);
-  switch (g_attn_exp_mode & 3) {
-    case 0: attn_fwd_kernel<0, 1><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
-    case 1: attn_fwd_kernel<1, 1><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
-    case 2: attn_fwd_kernel<0, 2><<<grid, 320, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
-    default: attn_fwd_kernel<1, 2><<<grid, 320, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
+  switch (g_attn_exp_mode & 7) {
+    case 0: attn_fwd_kernel<0, 1, 0><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
+    case 1: attn_fwd_kernel<1, 1, 0><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
+    case 2: attn_fwd_kernel<0, 2, 0><<<grid, 320, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
+    case 3: attn_fwd_kernel<1, 2, 0><<<grid, 320, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
+    case 4: attn_fwd_kernel<0, 1, 1><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
+    default: attn_fwd_kernel<1, 1, 1><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
   }
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;

@@ -21,7 +21,7 @@ def _ref(qkv, B, T, D):
     (2, 4097, 1024, 1.0),   # 896 / 14 grid + cls (ViT-L)
     (1, 1000, 128, 4.0),    # peaky softmax: exercises the lazy-rescale path
 ])
-@pytest.mark.parametrize("exp_mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("exp_mode", [0, 1, 2, 3, 4, 5])
 def test_attention_matches_fp32(cuda_device, B, T, D, scale, exp_mode):
     from multihmr_b200 import ops
 
