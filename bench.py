@@ -54,47 +54,64 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md): the
+    sampler runs from before the warm-up, and only samples stamped inside [mark_start, mark_stop] count."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.t0, self.t1 = index, None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
+    def mark_start(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def mark_stop(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def stop(self) -> dict:
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, pw, reasons = [], [], [], set()
+        sm, mx, pw, reasons, n_all = [], [], [], set(), 0
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in out.strip().splitlines():
             f = [c.strip() for c in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                vals = (float(f[1]), float(f[2]), float(f[3]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            n_all += 1
+            if self.t0 is not None and not (self.t0 <= ts <= self.t1):
+                continue
+            sm.append(vals[0]); mx.append(vals[1]); pw.append(vals[2])
+            for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "samples_total": n_all,
+                    "reasons": ["no samples inside the timed region"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
                 "samples": len(sm), "reasons": sorted(reasons)}
 
@@ -211,7 +228,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         if sampler:
-            sampler.start()
+            sampler.mark_start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
@@ -219,6 +236,8 @@ def run_ours(args):
             last = fn()
         e1.record()
         torch.cuda.synchronize()
+        if sampler:
+            sampler.mark_stop()
         clocks = sampler.stop() if sampler else None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -228,10 +247,12 @@ def run_ours(args):
 
     # ---- device-resident throughput (value) with live per-kernel-family CUDA-event timing
     model.set_profiling(True)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     model.get_profile()  # drop warm-up records
-    ms_total, P_last, clocks = timed(step_device, args.steps, 0, ClockSampler(local))
+    ms_total, P_last, clocks = timed(step_device, args.steps, 0, sampler)
     prof = model.get_profile()
     launches = model.last_launch_count()
     model.set_profiling(False)
@@ -369,7 +390,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the (slow) CPU oracle leg")
