@@ -67,7 +67,7 @@ def _rotvec_to_rotmat(rv):
     return roma_ref.rotvec_to_rotmat(rv)
 
 
-def compare(got: dict, ref: dict, keys, focal=None, verbose=False):
+def compare(got: dict, ref: dict, keys, focal=None, verbose=False, tol_scale=1.0):
     """Returns list of (key, err, tol) that fail; prints a table when verbose."""
     bad = []
     for k in keys:
@@ -85,7 +85,9 @@ def compare(got: dict, ref: dict, keys, focal=None, verbose=False):
         tol = TOL.get(k, 1e-3)
         if tol is None:
             src = ref["j3d"] if k == "j2d" else ref["v3d"]
-            tol = projection_tolerance(src, focal)
+            tol = projection_tolerance(src, focal, tol3d=1e-3 * tol_scale)
+        else:
+            tol = tol * tol_scale
         if verbose:
             print(f"  {k:20s} max|ref|={r.abs().max().item() if r.numel() else 0:10.4f} err={err:.3e} tol={tol:.1e}"
                   f" {'OK' if err <= tol else 'FAIL'}")
