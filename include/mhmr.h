@@ -57,10 +57,8 @@ int mhmr_op_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int
 int mhmr_op_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int B, int T, int D,
                       void* stream);
 
-/* Attention kernel variant (mhmr_op_attention and the engine), a 2-bit mask:
- *   bit 0: three of eight softmax exponentials on the FMA pipes (cubic polynomial, relative error 7.5e-5,
- *          below the fp16 rounding of P) instead of MUFU.EX2;
- *   bit 1: two softmax threads per query row (8 softmax warps per CTA) instead of one. */
+/* Softmax exponentials of mhmr_op_attention / the engine: 0 = all on MUFU.EX2 (default), 1 = three of
+ * eight on the FMA pipes with a cubic polynomial (relative error 7.5e-5, below the fp16 rounding of P). */
 int mhmr_set_attention_exp_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------------

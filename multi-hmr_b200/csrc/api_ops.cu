@@ -36,7 +36,7 @@ int mhmr_op_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, i
 }
 
 int mhmr_set_attention_exp_mode(int mode) {
-  MHMR_REQUIRE(mode >= 0 && mode <= 5, "attention mode: bit0 polynomial exp offload, bit1 two threads per row, 4/5 software-pipelined");
+  MHMR_REQUIRE(mode == 0 || mode == 1, "attention mode: 0 = MUFU exponentials, 1 = MUFU + polynomial offload");
   attention_set_exp_mode(mode);
   return MHMR_OK;
 }

@@ -8,9 +8,16 @@
 //   TMEM  = 256 columns: S (128 fp32) | P (64 cols = 128 fp16, A operand of the PV MMA) | O (64 fp32)
 //   S = Q K^T : tcgen05.mma SS, M=128 N=128 K=64     (K tile K-major,  128B swizzle, via TMA)
 //   O += P V  : tcgen05.mma TS, M=128 N=64  K=128    (V tile MN-major, 128B swizzle, via TMA)
-// Online softmax in fp32 in the exp2 domain with lazy rescaling of O (only when the running max
-// grows by more than 2^8), so the O read-modify-write through tcgen05.ld/st is rare.
-#include "common.cuh"
+// Online softmax in fp32 in the exp2 domain (packed f32x2 FMA/ADD, 3-input max) with lazy rescaling of O
+// (only when the running max grows by more than 2^8), so the O read-modify-write through tcgen05.ld/st
+// is rare.  The binding pipe is MUFU.EX2 (16/clk/SM): one exponential per score against 512 tensor cycles
+// per 128x128 tile.
+//
+// Ragged sequence (T = N + 1 is 1 mod 128 for every Multi-HMR resolution):
+//   * the last key tile only computes the 16-column groups that hold real keys (QK^T with N = 16..128,
+//     PV with K = 16..128, softmax over the needed 32-column chunks);
+//   * softmax warps whose 32 query rows are all beyond T only keep the barrier protocol alive.
+#include "kernels.cuh"
 
 namespace mhmr {
 
@@ -20,8 +27,9 @@ constexpr int kHeadDim = 64;
 constexpr int kBlockQ = 128;
 constexpr int kBlockKV = 128;
 constexpr int kStagesKV = 2;
+constexpr int kAttnThreads = 192;
 constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: Q, K or V tile
-constexpr int kAttnSmem = kTileBytes * (1 + 2 * kStagesKV) + 4096 + 1024;  // tiles + barriers/exchange + align
+constexpr int kAttnSmem = kTileBytes * (1 + 2 * kStagesKV) + 1024 + 1024;  // tiles + barriers + align
 
 constexpr uint32_t kColS = 0;
 constexpr uint32_t kColP = 128;
@@ -52,22 +60,12 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   return r;
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// kSplit = softmax threads per query row (1: 4 softmax warps, 2: 8 softmax warps, each thread owning half
-// of the key columns of its row; the two threads of a row exchange their partial row max through smem).
-template <int kExpMode, int kSplit, int kPipe>
-__global__ void __launch_bounds__(64 + 128 * kSplit, 2)
+// kExpMode 0: every exponential on MUFU.EX2; 1: three pairs of eight on the FMA pipes (cubic polynomial,
+// relative error 7.5e-5, far below the fp16 rounding of P).
+template <int kExpMode>
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
                 int T, int D, float scale_log2) {
-  constexpr int kColsPerThread = kBlockKV / kSplit;  // S columns per softmax thread
-  constexpr int kChunks = kColsPerThread / 32;
-  constexpr int kOCols = kHeadDim / kSplit;          // O columns per softmax thread
-  constexpr int kOChunks = kOCols / 32;
-  constexpr int kSoftmaxWarps = 4 * kSplit;
-
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -84,7 +82,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   uint64_t* p_full = s_empty + 1;          // softmax -> MMA : P_j in TMEM (and O rescaled)
   uint64_t* pv_done = p_full + 1;          // MMA -> softmax : O += P_j V_j complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
-  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [2][2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,6 +89,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   const int row0 = img * T;              // first token row of this image in the [B*T, 3D] matrix
   const int q0 = q_tile * kBlockQ;
   const int n_kv = (T + kBlockKV - 1) / kBlockKV;
+  // real keys of the last tile, rounded up to the 16-column granularity of the MMAs
+  const int last_valid = T - (n_kv - 1) * kBlockKV;
+  const int last_cols = (last_valid + 15) & ~15;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -103,8 +103,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         mbar_init(&kv_empty[s], 1);
       }
       mbar_init(s_full, 1);
-      mbar_init(s_empty, kSoftmaxWarps);
-      mbar_init(p_full, kSoftmaxWarps);
+      mbar_init(s_empty, 4);
+      mbar_init(p_full, 4);
       mbar_init(pv_done, 1);
       fence_barrier_init();
     }
@@ -135,7 +135,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, false, true);  // B (V) is MN-major
       const uint32_t t_s = tmem_base + kColS;
       const uint32_t t_p = tmem_base + kColP;
@@ -144,6 +143,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
 
       auto issue_qk = [&](int j) {
         const int s = j % kStagesKV;
+        const int ncols = (j == n_kv - 1) ? last_cols : kBlockKV;
+        const uint32_t idesc_qk = make_idesc_f16(128, ncols, false, false);
         mbar_wait(&k_full[s], (j / kStagesKV) & 1u);
         tc_fence_after();
         const uint64_t k_desc = make_sw128_desc(smem_u32(sK + s * kTileBytes), 16, 1024);
@@ -167,8 +168,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         tc_fence_after();
         // V tile: 128 keys (K) x 64 dims (N), N contiguous: MN-major, 8-key groups 1024 B apart.
         const uint64_t v_desc = make_sw128_desc(smem_u32(sV + s * kTileBytes), 1024, 1024);
-#pragma unroll
-        for (int k = 0; k < kBlockKV / 16; ++k) {
+        const int ksteps = ((j == n_kv - 1) ? last_cols : kBlockKV) / 16;
+        for (int k = 0; k < ksteps; ++k) {
           // A: 16 fp16 of P = 8 TMEM columns per K step; B: 16 keys = 2048 B per K step
           umma_f16_ts(t_o, t_p + 8u * k, v_desc + 128u * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         }
@@ -179,57 +180,63 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   } else {
     // ------------------------------ Softmax warps ------------------------------
     const int sub = warp & 3;             // TMEM sub-partition (lane quarter) of this warp
-    const int half = (warp - 2) >> 2;     // which column half of the row (always 0 when kSplit == 1)
     const int row = sub * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(sub * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_base + kColS + half * kColsPerThread;
-    const uint32_t t_p = tmem_base + lane_base + kColP + half * (kColsPerThread / 2);
-    const uint32_t t_o = tmem_base + lane_base + kColO + half * kOCols;
-    const int col_base = half * kColsPerThread;
+    const uint32_t t_s = tmem_base + lane_base + kColS;
+    const uint32_t t_p = tmem_base + lane_base + kColP;
+    const uint32_t t_o = tmem_base + lane_base + kColO;
+    const bool warp_has_rows = (q0 + sub * 32) < T;  // warp-uniform
 
-    float m_used = -INFINITY;  // running max (log2 domain) actually used as the exponent offset
-    float l = 0.0f;            // (partial, per thread) running row sum
+    if (!warp_has_rows) {
+      // All 32 rows of this warp are beyond the sequence: their S/P/O lanes hold garbage that is never
+      // stored and never mixes with other rows (the MMAs are row-independent); keep the protocol alive.
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(s_full, j & 1u);
+        if (lane == 0) mbar_arrive(s_empty);
+        if (j > 0) mbar_wait(pv_done, (j - 1) & 1u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      mbar_wait(pv_done, (n_kv - 1) & 1u);
+    } else {
+      float m_used = -INFINITY;  // running max (log2 domain) actually used as the exponent offset
+      float l = 0.0f;
 
-    if constexpr (kPipe == 1) {
-      // Software-pipelined variant (one thread per row): while the exponentials of tile j are being
-      // computed, the scores of tile j+1 are already streamed from TMEM into the registers freed chunk by
-      // chunk, so that the only non-MUFU phase left between two tiles is the row-max reduction.
-      static_assert(kSplit == 1, "pipelined softmax uses one thread per row");
-      uint32_t s[4][32];
-      auto tile_max = [&](int jt) -> float {
-        if (jt == n_kv - 1) {  // only the last tile can hold keys beyond T (or rows of the next image)
-          const int valid = T - jt * kBlockKV;
-          if (valid < kBlockKV) {
+      for (int j = 0; j < n_kv; ++j) {
+        const bool is_last = (j == n_kv - 1);
+        const int nch = is_last ? ((last_cols + 31) >> 5) : 4;  // 32-column chunks that matter (uniform)
+        mbar_wait(s_full, j & 1u);
+        tc_fence_after();
+        uint32_t s[4][32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 4; ++c)
+          if (c < nch) tmem_ld_32x32(t_s + c * 32, s[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty);
+
+        if (is_last && last_valid < kBlockKV) {  // keys beyond T (or rows of the next image): -inf
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
-          }
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= last_valid) s[c][i] = 0xff800000u;
         }
+        // row max: four independent chains (3-input max), then combine
         float mxa[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
+          float m0 = -INFINITY;
+          if (c < nch) {
+            m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
 #pragma unroll
-          for (int i = 2; i < 32; i += 2)
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+            for (int i = 2; i < 32; i += 2)
+              m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+          }
           mxa[c] = m0;
         }
-        return fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-      };
-      mbar_wait(s_full, 0);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
-      float mx = tile_max(0);
-
-      for (int j = 0; j < n_kv; ++j) {
-        const bool has_next = (j + 1) < n_kv;
+        const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
         const float m_new = fmaxf(m_used, mx * scale_log2);
         const bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile
         float alpha = 1.0f;
@@ -237,10 +244,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
           alpha = exp2f(m_used - m_new);  // 0 on the first tile
           m_used = m_new;
         }
+        // exponentials (MUFU.EX2 is the binding pipe), packed f32x2 FMA/ADD, two accumulator pairs
+        const float2 sc2 = make_float2(scale_log2, scale_log2);
+        const float2 nm2 = make_float2(-m_used, -m_used);
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        uint32_t p[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nch) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+              const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+              const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
+              const bool poly0 = (kExpMode == 1) && (pair == 0 || pair == 4);
+              const bool poly1 = (kExpMode == 1) && (pair + 1 == 3);
+              const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
+              const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
+              acc0 = __fadd2_rn(acc0, e0);
+              acc1 = __fadd2_rn(acc1, e1);
+              const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
+              p[c][i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
+              p[c][i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+            }
+          }
+        }
+        l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
+
         if (j > 0) {
           mbar_wait(pv_done, (j - 1) & 1u);  // P buffer free, O stable
           tc_fence_after();
-          if (__any_sync(0xffffffffu, rescale)) {
+          if (__any_sync(0xffffffffu, rescale)) {  // rare after the first tiles: small chunks
 #pragma unroll 1
             for (int c = 0; c < kHeadDim / 8; ++c) {
               uint32_t o[8];
@@ -252,174 +286,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
             }
           }
         }
-        const float2 sc2 = make_float2(scale_log2, scale_log2);
-        const float2 nm2 = make_float2(-m_used, -m_used);
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t p[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
-            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
-            const int pair = (i >> 1) & 7;
-            const bool poly0 = (kExpMode == 1) && (pair == 0 || pair == 4);
-            const bool poly1 = (kExpMode == 1) && (pair + 1 == 3);
-            const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
-            const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
-            acc0 = __fadd2_rn(acc0, e0);
-            acc1 = __fadd2_rn(acc1, e1);
-            const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
-            p[i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
-            p[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-          }
-          tmem_st_32x16(t_p + c * 16, p);
-          if (has_next) {
-            if (c == 1) {  // S_{j+1} was issued when this thread released S_j, one tile ago
-              mbar_wait(s_full, (j + 1) & 1u);
-              tc_fence_after();
-            }
-            if (c >= 1) tmem_ld_32x32(t_s + (c - 1) * 32, s[c - 1]);  // registers of chunk c-1 are free
-          }
-        }
-        l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
+        for (int c = 0; c < 4; ++c)
+          if (c < nch) tmem_st_32x16(t_p + c * 16, p[c]);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
-        if (has_next) {
-          tmem_ld_32x32(t_s + 3 * 32, s[3]);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_empty);
-          mx = tile_max(j + 1);
-        }
       }
-    } else {
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1u);
+
+      // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
+      mbar_wait(pv_done, (n_kv - 1) & 1u);
       tc_fence_after();
-      uint32_t s[kChunks][32];
+      const float inv_l = 1.0f / l;
+      const int q = q0 + row;
+      __half* dst = out + static_cast<int64_t>(row0 + q) * ldo + head * kHeadDim;
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
-
-      if (j == n_kv - 1) {  // only the last tile can hold keys beyond T (or rows of the next image)
-        const int valid = T - j * kBlockKV;
-        if (valid < kBlockKV) {
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32(t_o + c * 32, o);
+        tmem_ld_wait();
+        if (q < T) {
 #pragma unroll
-          for (int c = 0; c < kChunks; ++c)
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col_base + c * 32 + i >= valid) s[c][i] = 0xff800000u;  // -inf
-        }
-      }
-      // row max: independent chains (3-input max), then combine
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
-#pragma unroll
-        for (int i = 2; i < 32; i += 2)
-          m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
-        mx = fmaxf(mx, m0);
-      }
-      if constexpr (kSplit == 2) {
-        float* x = xch + (j & 1) * 256;
-        x[half * 128 + row] = mx;
-        named_bar_sync(1 + sub, 64);
-        mx = fmaxf(mx, x[(1 - half) * 128 + row]);
-      }
-      const float m_new = fmaxf(m_used, mx * scale_log2);
-      const bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile (m_used = -inf)
-      float alpha = 1.0f;
-      if (rescale) {
-        alpha = exp2f(m_used - m_new);  // 0 on the first tile
-        m_used = m_new;
-      }
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1u);  // P buffer free, O stable
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, rescale)) {  // rare after the first tiles: small chunks, few registers
-#pragma unroll 1
-          for (int c = 0; c < kOCols / 8; ++c) {
-            uint32_t o[8];
-            tmem_ld_32x8(t_o + c * 8, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x8(t_o + c * 8, o);
+            for (int i = 0; i < 4; ++i) {
+              const __half2 h = __floats2half2_rn(__uint_as_float(o[g * 8 + 2 * i]) * inv_l,
+                                                  __uint_as_float(o[g * 8 + 2 * i + 1]) * inv_l);
+              pw[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
           }
-        }
-      }
-      // exponentials: MUFU.EX2 (16/clk/SM) is the binding pipe for head dim 64, so in kExpMode 1 three
-      // pairs out of eight are evaluated on the FMA pipes instead (Cody-Waite + cubic, rel. err 7.5e-5,
-      // far below the fp16 rounding of P).  Packed f32x2 FMA/ADD, two independent accumulator pairs.
-      const float2 sc2 = make_float2(scale_log2, scale_log2);
-      const float2 nm2 = make_float2(-m_used, -m_used);
-      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        uint32_t p[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
-          const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
-          const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
-          const bool poly0 = (kExpMode == 1) && (pair == 0 || pair == 4);
-          const bool poly1 = (kExpMode == 1) && (pair + 1 == 3);
-          const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
-          const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
-          acc0 = __fadd2_rn(acc0, e0);
-          acc1 = __fadd2_rn(acc1, e1);
-          const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
-          p[i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
-          p[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-        }
-        tmem_st_32x16(t_p + c * 16, p);
-      }
-      l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-
-    }
-
-    // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
-    mbar_wait(pv_done, (n_kv - 1) & 1u);
-    tc_fence_after();
-    if constexpr (kSplit == 2) {
-      float* x = xch + (n_kv & 1) * 256;
-      x[half * 128 + row] = l;
-      named_bar_sync(1 + sub, 64);
-      l += x[(1 - half) * 128 + row];
-    }
-    const float inv_l = 1.0f / l;
-    const int q = q0 + row;
-    __half* dst = out + static_cast<int64_t>(row0 + q) * ldo + head * kHeadDim + half * kOCols;
-#pragma unroll
-    for (int c = 0; c < kOChunks; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32(t_o + c * 32, o);
-      tmem_ld_wait();
-      if (q < T) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __half2 h = __floats2half2_rn(__uint_as_float(o[g * 8 + 2 * i]) * inv_l,
-                                                __uint_as_float(o[g * 8 + 2 * i + 1]) * inv_l);
-            pw[i] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
         }
       }
     }
@@ -452,24 +351,16 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   if (rc != MHMR_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     attr_set = true;
   }
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   dim3 grid((T + kBlockQ - 1) / kBlockQ, D / kHeadDim, B);
-  switch (g_attn_exp_mode & 7) {
-    case 0: attn_fwd_kernel<0, 1, 0><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
-    case 1: attn_fwd_kernel<1, 1, 0><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
-    case 2: attn_fwd_kernel<0, 2, 0><<<grid, 320, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
-    case 3: attn_fwd_kernel<1, 2, 0><<<grid, 320, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
-    case 4: attn_fwd_kernel<0, 1, 1><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
-    default: attn_fwd_kernel<1, 1, 1><<<grid, 192, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2); break;
-  }
+  if (g_attn_exp_mode == 1)
+    attn_fwd_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2);
+  else
+    attn_fwd_kernel<0><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2);
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }

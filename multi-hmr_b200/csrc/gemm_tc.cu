@@ -65,7 +65,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
                     v1.x + b1.x, v1.y + b1.y, v1.z + b1.z, v1.w + b1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if constexpr (EPI == EPI_BIAS_GELU_F16) x[i] = gelu_erf(x[i]);
+        if constexpr (EPI == EPI_BIAS_GELU_F16) x[i] = gelu_erf_fast(x[i]);
         if constexpr (EPI == EPI_BIAS_RELU_F16) x[i] = fmaxf(x[i], 0.0f);
       }
       const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);

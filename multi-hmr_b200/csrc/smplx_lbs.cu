@@ -88,31 +88,40 @@ smplx_prep_kernel(const float* __restrict__ rotvec, const float* __restrict__ sh
   }
   if (j < L) cf[static_cast<int64_t>(p) * KT + kPoseFeat + j] = beta[j];
   __syncthreads();
-  if (j == 0) {
-    // kinematic chain (smplx.lbs.batch_rigid_transform): G_i = G_parent [R_i | J_i - J_parent]
-    for (int i = 0; i < kNJ; ++i) {
-      const int par = parents[i];
-      float t[3] = {Js[i][0], Js[i][1], Js[i][2]};
-      if (i == 0 || par < 0) {
+  if (j < kNJ) {
+    // kinematic chain (smplx.lbs.batch_rigid_transform): G_j = prod over the ancestors (root first) of
+    // [R_i | J_i - J_parent(i)].  Every joint walks its own ancestor list (depth <= 16) independently
+    // instead of one thread serialising the 55 joints; the product order equals the reference's.
+    int anc[16];
+    int depth = 0;
+    for (int a = j; a >= 0 && depth < 16; a = parents[a]) anc[depth++] = a;
+    float G[12];
+    {
+      const int r0 = anc[depth - 1];  // root
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          Gs[i][r * 4 + 0] = Rs[i][r * 3 + 0];
-          Gs[i][r * 4 + 1] = Rs[i][r * 3 + 1];
-          Gs[i][r * 4 + 2] = Rs[i][r * 3 + 2];
-          Gs[i][r * 4 + 3] = t[r];
-        }
-      } else {
-        t[0] -= Js[par][0]; t[1] -= Js[par][1]; t[2] -= Js[par][2];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float g0 = Gs[par][r * 4], g1 = Gs[par][r * 4 + 1], g2 = Gs[par][r * 4 + 2];
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            Gs[i][r * 4 + c] = g0 * Rs[i][c] + g1 * Rs[i][3 + c] + g2 * Rs[i][6 + c];
-          Gs[i][r * 4 + 3] = g0 * t[0] + g1 * t[1] + g2 * t[2] + Gs[par][r * 4 + 3];
-        }
+      for (int r = 0; r < 3; ++r) {
+        G[r * 4 + 0] = Rs[r0][r * 3 + 0];
+        G[r * 4 + 1] = Rs[r0][r * 3 + 1];
+        G[r * 4 + 2] = Rs[r0][r * 3 + 2];
+        G[r * 4 + 3] = Js[r0][r];
       }
     }
+    for (int d = depth - 2; d >= 0; --d) {
+      const int i = anc[d], par = anc[d + 1];
+      const float t0 = Js[i][0] - Js[par][0], t1 = Js[i][1] - Js[par][1], t2 = Js[i][2] - Js[par][2];
+      float H[12];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float g0 = G[r * 4], g1 = G[r * 4 + 1], g2 = G[r * 4 + 2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) H[r * 4 + c] = g0 * Rs[i][c] + g1 * Rs[i][3 + c] + g2 * Rs[i][6 + c];
+        H[r * 4 + 3] = g0 * t0 + g1 * t1 + g2 * t2 + G[r * 4 + 3];
+      }
+#pragma unroll
+      for (int q = 0; q < 12; ++q) G[q] = H[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 12; ++q) Gs[j][q] = G[q];
   }
   __syncthreads();
   if (j < kNJ) {
@@ -163,12 +172,15 @@ smplx_prep_kernel(const float* __restrict__ rotvec, const float* __restrict__ sh
 
 // ------------------------------------------------------------------------------------------------
 // Vertex kernel: v_posed = v_template + cf . PDX ; skinning ; root placement ; optional projection.
+//   thread = (column group of 4 coordinates, k-slice): the 8 k-slices of a column group are 8 adjacent lanes,
+//   slice s streams rows k = s, s+8, ... with 8 independent 128-bit loads in flight, 16 persons are
+//   accumulated per streamed row, and the slices are folded with warp shuffles (no smem round trip).
 // ------------------------------------------------------------------------------------------------
 constexpr int kTV = 72;          // vertices per CTA
 constexpr int kTC = kTV * 3;     // 216 columns
 constexpr int kCG = kTC / 4;     // 54 float4 column groups
-constexpr int kKS = 8;           // k-slices
-constexpr int kPB = 8;           // persons per pass
+constexpr int kKS = 8;           // k-slices = adjacent lanes
+constexpr int kPB = 16;          // persons per pass
 constexpr int kVertThreads = kCG * kKS;  // 432
 constexpr int kKTMax = 512;      // >= 486 + 21
 
@@ -178,12 +190,19 @@ struct VertSmem {
   float xf[kPB][16];
   float tr[kPB][4];
   float Kd[kPB][12];
-  float red[kKS][kPB][kTC];
   float vps[kPB][kTC];
   float outs[kPB][kTC];
   float outs2[kPB][kTV * 2];
   float Ws[kTV][kNJ];
 };
+
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
 
 __global__ void __launch_bounds__(kVertThreads, 1)
 smplx_vertex_kernel(const float* __restrict__ PDX, int ldp, int KT, const float* __restrict__ vt,
@@ -201,10 +220,9 @@ smplx_vertex_kernel(const float* __restrict__ PDX, int ldp, int KT, const float*
   const int col0 = v0 * 3;
   const int nv = min(kTV, V - v0);
   const int ncol = nv * 3;
-  const int slice = tid / kCG, cg = tid - slice * kCG;
-  const int rows_per_slice = (KT + kKS - 1) / kKS;
-  const int k_beg = slice * rows_per_slice, k_end = min(KT, k_beg + rows_per_slice);
+  const int cg = tid >> 3, slice = tid & 7;
   const bool col_ok = (col0 + cg * 4) < ldp;
+  const int n_iter = (KT + kKS - 1) / kKS;
 
   for (int i = tid; i < kTV * kNJ; i += kVertThreads) {
     const int v = i / kNJ, jj = i - v * kNJ;
@@ -222,19 +240,15 @@ smplx_vertex_kernel(const float* __restrict__ PDX, int ldp, int KT, const float*
       const int j = i / (kNJ * 12), r = i - j * (kNJ * 12);
       sm.As[j][r] = (j < np) ? Amat[static_cast<int64_t>(pb0 + j) * kNJ * 12 + r] : 0.f;
     }
-    if (tid < kPB * 16) {
-      const int j = tid / 16, r = tid & 15;
+    for (int i = tid; i < kPB * 16; i += kVertThreads) {
+      const int j = i >> 4, r = i & 15;
       sm.xf[j][r] = (j < np) ? xf[static_cast<int64_t>(pb0 + j) * 16 + r] : 0.f;
-    } else if (tid < kPB * 16 + kPB * 4) {
-      const int t = tid - kPB * 16, j = t / 4, r = t & 3;
-      sm.tr[j][r] = (j < np && r < 3) ? transl[(pb0 + j) * 3 + r] : 0.f;
-    } else if (tid < kPB * 16 + kPB * 4 + kPB * 9) {
-      const int t = tid - kPB * 20, j = t / 9, r = t - j * 9;
-      sm.Kd[j][r] = (j < np) ? K_det[(pb0 + j) * 9 + r] : 0.f;
+      if (r < 4) sm.tr[j][r] = (j < np && r < 3) ? transl[(pb0 + j) * 3 + r] : 0.f;
+      if (r < 9) sm.Kd[j][r] = (j < np) ? K_det[(pb0 + j) * 9 + r] : 0.f;
     }
     __syncthreads();
 
-    // ---- stream the PDX tile: acc[i][j] += cf[j][k] * PDX[k][col + i]
+    // ---- stream the PDX tile: acc[i][j] += cf[j][k] * PDX[k][col + i], rows k = slice, slice+8, ...
     float acc[4][kPB];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -242,34 +256,52 @@ smplx_vertex_kernel(const float* __restrict__ PDX, int ldp, int KT, const float*
       for (int j = 0; j < kPB; ++j) acc[i][j] = 0.f;
     if (col_ok) {
       const float* src = PDX + col0 + cg * 4;
-#pragma unroll 4
-      for (int k = k_beg; k < k_end; ++k) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(k) * ldp));
-        const float4 c0 = *reinterpret_cast<const float4*>(&sm.pfs[k][0]);
-        const float4 c1 = *reinterpret_cast<const float4*>(&sm.pfs[k][4]);
-        const float cj[kPB] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll 1
+      for (int it0 = 0; it0 < n_iter; it0 += 8) {
+        float4 w[8];
 #pragma unroll
-        for (int j = 0; j < kPB; ++j) {
-          acc[0][j] = fmaf(cj[j], w.x, acc[0][j]);
-          acc[1][j] = fmaf(cj[j], w.y, acc[1][j]);
-          acc[2][j] = fmaf(cj[j], w.z, acc[2][j]);
-          acc[3][j] = fmaf(cj[j], w.w, acc[3][j]);
+        for (int u = 0; u < 8; ++u) {
+          const int k = (it0 + u) * kKS + slice;
+          w[u] = (k < KT) ? ldg_stream(src + static_cast<int64_t>(k) * ldp) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = min((it0 + u) * kKS + slice, KT - 1);  // w is zero when k is out of range
+#pragma unroll
+          for (int q = 0; q < kPB / 4; ++q) {
+            const float4 c = *reinterpret_cast<const float4*>(&sm.pfs[k][q * 4]);
+            const float cj[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[0][q * 4 + j] = fmaf(cj[j], w[u].x, acc[0][q * 4 + j]);
+              acc[1][q * 4 + j] = fmaf(cj[j], w[u].y, acc[1][q * 4 + j]);
+              acc[2][q * 4 + j] = fmaf(cj[j], w[u].z, acc[2][q * 4 + j]);
+              acc[3][q * 4 + j] = fmaf(cj[j], w[u].w, acc[3][q * 4 + j]);
+            }
+          }
         }
       }
     }
+    // ---- fold the 8 k-slices (adjacent lanes), add the template; lane s keeps persons 2s, 2s+1
 #pragma unroll
-    for (int j = 0; j < kPB; ++j)
-      *reinterpret_cast<float4*>(&sm.red[slice][j][cg * 4]) =
-          make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
-    __syncthreads();
-
-    // ---- reduce the k-slices, add the template
-    for (int i = tid; i < kPB * kTC; i += kVertThreads) {
-      const int j = i / kTC, c = i - j * kTC;
-      float s = 0.f;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int sl = 0; sl < kKS; ++sl) s += sm.red[sl][j][c];
-      sm.vps[j][c] = (c < ncol) ? (vt[col0 + c] + s) : 0.f;
+      for (int j = 0; j < kPB; ++j) {
+        float v = acc[i][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        acc[i][j] = v;
+      }
+#pragma unroll
+    for (int j = 0; j < kPB; ++j) {
+      if ((j >> 1) == slice) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = cg * 4 + i;
+          sm.vps[j][c] = (c < ncol) ? (vt[col0 + c] + acc[i][j]) : 0.f;
+        }
+      }
     }
     __syncthreads();
 

@@ -20,8 +20,12 @@ def _ref(qkv, B, T, D):
     (1, 2305, 384, 1.0),    # 672 / 14 grid + cls (ViT-S)
     (2, 4097, 1024, 1.0),   # 896 / 14 grid + cls (ViT-L)
     (1, 1000, 128, 4.0),    # peaky softmax: exercises the lazy-rescale path
+    (1, 128 + 17, 64, 1.0), # tail of 17 keys: two 16-column groups, one 32-column chunk
+    (1, 256 + 40, 64, 1.0), # tail of 40 keys: 48 columns, two chunks
+    (1, 384 + 100, 64, 1.0),# tail of 100 keys: 112 columns, four chunks
+    (1, 33, 64, 1.0),       # one short tile, query warps 2..3 have no rows
 ])
-@pytest.mark.parametrize("exp_mode", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("exp_mode", [0, 1])
 def test_attention_matches_fp32(cuda_device, B, T, D, scale, exp_mode):
     from multihmr_b200 import ops
 
