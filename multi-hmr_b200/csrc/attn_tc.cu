@@ -17,6 +17,8 @@
 //   * the last key tile only computes the 16-column groups that hold real keys (QK^T with N = 16..128,
 //     PV with K = 16..128, softmax over the needed 32-column chunks);
 //   * softmax warps whose 32 query rows are all beyond T only keep the barrier protocol alive.
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace mhmr {
@@ -202,41 +204,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
       float m_used = -INFINITY;  // running max (log2 domain) actually used as the exponent offset
       float l = 0.0f;
 
-      for (int j = 0; j < n_kv; ++j) {
-        const bool is_last = (j == n_kv - 1);
-        const int nch = is_last ? ((last_cols + 31) >> 5) : 4;  // 32-column chunks that matter (uniform)
+      // One key tile of the online softmax with NCH (compile-time) 32-column chunks: 4 for full tiles, fewer
+      // for the ragged last tile.  Static chunk counts keep the 128 scores in registers (no local memory).
+      auto softmax_tile = [&](auto nch_c, int j) {
+        constexpr int NCH = decltype(nch_c)::value;
         mbar_wait(s_full, j & 1u);
         tc_fence_after();
-        uint32_t s[4][32];
+        uint32_t s[NCH][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < nch) tmem_ld_32x32(t_s + c * 32, s[c]);
+        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);
 
-        if (is_last && last_valid < kBlockKV) {  // keys beyond T (or rows of the next image): -inf
+        if (NCH < 4 || last_valid < kBlockKV) {
+          if (j == n_kv - 1) {  // keys beyond T (or rows of the next image): -inf
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < NCH; ++c)
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= last_valid) s[c][i] = 0xff800000u;
-        }
-        // row max: four independent chains (3-input max), then combine
-        float mxa[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float m0 = -INFINITY;
-          if (c < nch) {
-            m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
-#pragma unroll
-            for (int i = 2; i < 32; i += 2)
-              m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i >= last_valid) s[c][i] = 0xff800000u;
           }
-          mxa[c] = m0;
         }
-        const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+        // row max: independent chains (3-input max), then combine
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
+#pragma unroll
+          for (int i = 2; i < 32; i += 2)
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+          mx = fmaxf(mx, m0);
+        }
         const float m_new = fmaxf(m_used, mx * scale_log2);
         const bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile
         float alpha = 1.0f;
@@ -248,25 +248,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         const float2 sc2 = make_float2(scale_log2, scale_log2);
         const float2 nm2 = make_float2(-m_used, -m_used);
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-        uint32_t p[4][16];
+        uint32_t p[NCH][16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nch) {
+        for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
-              const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
-              const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
-              const bool poly0 = (kExpMode == 1) && (pair == 0 || pair == 4);
-              const bool poly1 = (kExpMode == 1) && (pair + 1 == 3);
-              const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
-              const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
-              acc0 = __fadd2_rn(acc0, e0);
-              acc1 = __fadd2_rn(acc1, e1);
-              const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
-              p[c][i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
-              p[c][i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-            }
+          for (int i = 0; i < 32; i += 4) {
+            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
+            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
+            const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
+            const bool poly0 = (kExpMode == 1) && (pair == 0 || pair == 4);
+            const bool poly1 = (kExpMode == 1) && (pair + 1 == 3);
+            const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
+            const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
+            acc0 = __fadd2_rn(acc0, e0);
+            acc1 = __fadd2_rn(acc1, e1);
+            const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
+            p[c][i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
+            p[c][i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
           }
         }
         l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
@@ -287,12 +285,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
           }
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < nch) tmem_st_32x16(t_p + c * 16, p[c]);
+        for (int c = 0; c < NCH; ++c) tmem_st_32x16(t_p + c * 16, p[c]);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+      };
+
+      const int last_nch = (last_cols + 31) >> 5;  // 32-column chunks of the last tile that hold real keys
+      for (int j = 0; j < n_kv - 1; ++j) softmax_tile(std::integral_constant<int, 4>{}, j);
+      switch (last_nch) {
+        case 1: softmax_tile(std::integral_constant<int, 1>{}, n_kv - 1); break;
+        case 2: softmax_tile(std::integral_constant<int, 2>{}, n_kv - 1); break;
+        case 3: softmax_tile(std::integral_constant<int, 3>{}, n_kv - 1); break;
+        default: softmax_tile(std::integral_constant<int, 4>{}, n_kv - 1); break;
       }
 
       // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
