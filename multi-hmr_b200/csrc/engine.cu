@@ -377,9 +377,7 @@ int run_plan(mhmr_engine* e, int cat, GemmPlan& plan, int M, cudaStream_t st) {
   ProfScope ps_(e, cat, st);
   GemmPlan p = plan;  // tensor maps were built for the maximum M; the kernel bounds rows by p.M
   p.M = M;
-  const int tiles = ((M + 127) / 128) * ((p.N + p.bn - 1) / p.bn);
-  const int sms = device_sm_count();
-  p.grid = tiles < sms ? tiles : sms;
+  p.grid = gemm_plan_grid(&p, M);
   TRY(gemm_plan_run(&p, st));
   ++e->launches;
   return MHMR_OK;
@@ -414,7 +412,8 @@ int head_forward(mhmr_engine* e, const float* K, int B, float det_thresh, int nm
   const int D = e->D, N = e->N, res = e->res, Pm = e->cfg.max_persons, Cq = e->Cq, nb = e->cfg.num_betas;
   const int heads = e->cfg.xat_num_heads, inner = heads * 32, BN = B * N;
   int* det_b = o->det_idx; int* det_y = o->det_idx + Pm; int* det_x = o->det_idx + 2 * Pm;
-  int* count = o->count;
+  int* count_true = o->count;   // true number of detections (may exceed max_persons: reported as an error)
+  int* count = e->count + 2;    // clamped to max_persons: what the per-person kernels iterate over
   LAUNCH(MHMR_CAT_HEAD, invert_K(K, e->Kinv, B, st));
   LAUNCH(MHMR_CAT_HEAD, ctx_fourier(e->Kinv, e->w("camera.freq_bands"), e->ctx16, e->Cp, B, res, D, e->Cp - D, st));
   // detection (model.py:133-158)
@@ -422,12 +421,12 @@ int head_forward(mhmr_engine* e, const float* K, int B, float det_thresh, int nm
   LAUNCH(MHMR_CAT_HEAD, rowdot_sigmoid(e->H16, D, e->w("mlp_classif.2.weight"), e->w("mlp_classif.2.bias"), e->scores_raw, BN, D, st));
   if (forced_idx != nullptr) {
     LAUNCH(MHMR_CAT_HEAD, forced_detections(e->scores_raw, o->scores_map, B, res, forced_idx, forced_P, det_b, det_y, det_x,
-                         o->det_score, count, e->img_off, st));
+                         o->det_score, count_true, count, e->img_off, st));
   } else {
     LAUNCH(MHMR_CAT_HEAD, nms_compact(e->scores_raw, o->scores_map, B, res, nms, det_thresh, Pm, det_b, det_y, det_x,
-                       o->det_score, count, e->img_off, st));
+                       o->det_score, count_true, count, e->img_off, st));
   }
-  MHMR_CUDA_CHECK(cudaMemcpyAsync(e->h_count, count, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MHMR_CUDA_CHECK(cudaMemcpyAsync(e->h_count, count_true, sizeof(int), cudaMemcpyDeviceToHost, st));
   // keys / values of both decoder layers for every token (to_kv, cross_attn_transformer.py:187)
   TRY(run_plan(e, MHMR_CAT_GEMM_OTHER, e->kv_plan, BN, st));
   const std::string h = "x_attention_head.";

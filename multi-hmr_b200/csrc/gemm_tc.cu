@@ -9,6 +9,7 @@
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue), so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include "gemm_tc.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace mhmr {
 
@@ -19,9 +20,6 @@ constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + 32 * kEpiWarps;  // TMA, MMA, TMEM-alloc, spare + epilogue warps
-constexpr int kScratchStride = 36;               // floats per scratch row (32 + 4: conflict-free float4)
-constexpr int kScratchBytes = 32 * kScratchStride * 4;
-
 template <int BN>
 struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 3 : 5;
@@ -33,97 +31,6 @@ struct GemmCfg {
       kStages * kStageBytes + kEpiWarps * kScratchBytes + kBarBytes + 1024;  // +1024: manual align
   static constexpr int kTmemCols = 2 * BN;                                  // 256 or 512
 };
-
-// The accumulator chunk (32 rows x 32 columns, one row per thread after tcgen05.ld) is transposed through
-// a per-warp smem scratch so that global memory is accessed with lanes along the contiguous dimension:
-//   fp32 outputs: 8 lanes x float4 cover one 128-byte row segment, 4 rows per warp instruction;
-//   fp16 outputs: 4 lanes x (8 halves) cover one 64-byte row segment, 8 rows per warp instruction.
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* scratch, const GemmEpi& ep,
-                                               int M, int N, int m_base, int n0, int lane) {
-  constexpr bool kF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_RELU_F16);
-  // (a) rows -> scratch
-  float* my = scratch + lane * kScratchStride;
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<float4*>(my + q * 4) =
-        make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                    __uint_as_float(r[q * 4 + 3]));
-  __syncwarp();
-  if constexpr (kF16) {
-    const int cg = lane & 3, rs = lane >> 2;  // 8 columns per lane, 8 rows per instruction
-    const int n = n0 + cg * 8;
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int rl = k * 8 + rs;
-      const int m = m_base + rl;
-      const float4 v0 = *reinterpret_cast<const float4*>(scratch + rl * kScratchStride + cg * 8);
-      const float4 v1 = *reinterpret_cast<const float4*>(scratch + rl * kScratchStride + cg * 8 + 4);
-      float x[8] = {v0.x + b0.x, v0.y + b0.y, v0.z + b0.z, v0.w + b0.w,
-                    v1.x + b1.x, v1.y + b1.y, v1.z + b1.z, v1.w + b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if constexpr (EPI == EPI_BIAS_GELU_F16) x[i] = gelu_erf_fast(x[i]);
-        if constexpr (EPI == EPI_BIAS_RELU_F16) x[i] = fmaxf(x[i], 0.0f);
-      }
-      const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
-      const __half2 h2 = __floats2half2_rn(x[4], x[5]), h3 = __floats2half2_rn(x[6], x[7]);
-      uint4 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-      pk.z = *reinterpret_cast<const uint32_t*>(&h2);
-      pk.w = *reinterpret_cast<const uint32_t*>(&h3);
-      if (m < M)
-        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out) + static_cast<int64_t>(m) * ep.ldo + n) = pk;
-    }
-  } else {
-    const int cg = lane & 7, rs = lane >> 3;  // 4 columns per lane, 4 rows per instruction
-    const int n = n0 + cg * 4;
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(1.f, 1.f, 1.f, 1.f);
-    if constexpr (EPI == EPI_LS_RESID_F32) {
-      b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-      g = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
-    } else if constexpr (EPI == EPI_BIAS_F32) {
-      if (ep.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-    }
-    float* outp[8];
-    float4 xres[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int m = m_base + k * 4 + rs;
-      int64_t orow = m;
-      if constexpr (EPI == EPI_ROWADD_F32) {
-        const int grp = m / ep.rows_in, rin = m - grp * ep.rows_in;
-        orow = static_cast<int64_t>(grp) * ep.rows_out + ep.row_off + rin;
-        xres[k] = (m < M) ? __ldg(reinterpret_cast<const float4*>(ep.rowadd + static_cast<int64_t>(rin) * N + n))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      outp[k] = reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n;
-      if constexpr (EPI == EPI_LS_RESID_F32)
-        xres[k] = (m < M) ? *reinterpret_cast<const float4*>(outp[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int rl = k * 4 + rs;
-      const float4 v = *reinterpret_cast<const float4*>(scratch + rl * kScratchStride + cg * 4);
-      float4 a;
-      if constexpr (EPI == EPI_LS_RESID_F32) {
-        a.x = xres[k].x + g.x * (v.x + b.x);
-        a.y = xres[k].y + g.y * (v.y + b.y);
-        a.z = xres[k].z + g.z * (v.z + b.z);
-        a.w = xres[k].w + g.w * (v.w + b.w);
-      } else if constexpr (EPI == EPI_ROWADD_F32) {
-        a.x = v.x + xres[k].x; a.y = v.y + xres[k].y; a.z = v.z + xres[k].z; a.w = v.w + xres[k].w;
-      } else {
-        a.x = v.x + b.x; a.y = v.y + b.y; a.z = v.z + b.z; a.w = v.w + b.w;
-      }
-      if (m_base + rl < M) *reinterpret_cast<float4*>(outp[k]) = a;
-    }
-  }
-  __syncwarp();
-}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -298,7 +205,7 @@ int gemm_plan_init(GemmPlan* plan, const __half* A, int64_t lda, const __half* W
   MHMR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: row pitches must be multiples of 8 fp16 (16 B, TMA)");
   MHMR_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
                "gemm: operands must be 16-byte aligned");
-  MHMR_REQUIRE(bn == 128 || bn == 256, "gemm: BN must be 128 or 256");
+  MHMR_REQUIRE(bn == 128 || bn == 256 || bn == 512, "gemm: block_n must be 128, 256 or 512 (CTA pair)");
   MHMR_REQUIRE(epi_kind >= 0 && epi_kind < EPI_NUM_KINDS, "gemm: bad epilogue kind");
   MHMR_REQUIRE(ep.out != nullptr && ep.ldo % 8 == 0, "gemm: output missing or pitch not multiple of 8");
   if (epi_kind != EPI_BIAS_F32 && epi_kind != EPI_ROWADD_F32)
@@ -309,15 +216,27 @@ int gemm_plan_init(GemmPlan* plan, const __half* A, int64_t lda, const __half* W
   plan->M = M; plan->N = N; plan->K = K; plan->bn = bn; plan->epi = epi_kind; plan->ep = ep;
   int rc = make_tmap_2d(&plan->tmA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, M, K, lda * 2, BM, BK, true);
   if (rc != MHMR_OK) return rc;
-  rc = make_tmap_2d(&plan->tmB, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, N, K, ldw * 2, bn, BK, true);
+  // CTA pair: every CTA stages half (128 rows) of the 256-row weight tile
+  rc = make_tmap_2d(&plan->tmB, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, N, K, ldw * 2, bn == 512 ? 128 : bn, BK,
+                    true);
   if (rc != MHMR_OK) return rc;
-  const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
-  const int sms = device_sm_count();
-  plan->grid = tiles < sms ? tiles : sms;
+  plan->grid = gemm_plan_grid(plan, M);
   return MHMR_OK;
 }
 
+int gemm_plan_grid(const GemmPlan* plan, int M) {
+  const int sms = device_sm_count();
+  if (plan->bn == 512) {
+    const int tiles = ((M + 255) / 256) * ((plan->N + 255) / 256);
+    const int pairs = sms / 2;
+    return 2 * (tiles < pairs ? tiles : pairs);
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((plan->N + plan->bn - 1) / plan->bn);
+  return tiles < sms ? tiles : sms;
+}
+
 int gemm_plan_run(const GemmPlan* plan, cudaStream_t stream) {
+  if (plan->bn == 512) return gemm_plan_run_2cta(plan, stream);
   return plan->bn == 256 ? launch_bn<256>(plan, stream) : launch_bn<128>(plan, stream);
 }
 

@@ -38,7 +38,7 @@ struct GemmEpi {
 struct GemmPlan {
   CUtensorMap tmA, tmB;
   int M = 0, N = 0, K = 0;
-  int bn = 256;
+  int bn = 256;          // 128 / 256: single-CTA tile width; 512: CTA pair (cta_group::2), 256 x 256 tile
   int epi = EPI_BIAS_F16;
   GemmEpi ep;
   int grid = 0;
@@ -48,5 +48,8 @@ struct GemmPlan {
 int gemm_plan_init(GemmPlan* plan, const __half* A, int64_t lda, const __half* W, int64_t ldw, int M,
                    int N, int K, int epi_kind, const GemmEpi& ep, int bn);
 int gemm_plan_run(const GemmPlan* plan, cudaStream_t stream);
+int gemm_plan_run_2cta(const GemmPlan* plan, cudaStream_t stream);  // gemm_tc2.cu
+// launch geometry for `M` rows with this plan's tile shape
+int gemm_plan_grid(const GemmPlan* plan, int M);
 
 }  // namespace mhmr

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(1024, 1)
 nms_compact_kernel(const float* __restrict__ scores, float* __restrict__ scores_out, int B, int res,
                    int nms_k, float thresh, int max_persons, int* __restrict__ det_b,
                    int* __restrict__ det_y, int* __restrict__ det_x, float* __restrict__ det_score,
-                   int* __restrict__ count, int* __restrict__ img_off) {
+                   int* __restrict__ count, int* __restrict__ count_clamped, int* __restrict__ img_off) {
   __shared__ int warp_tot[32];
   __shared__ int base_s;
   const int N = res * res;
@@ -110,7 +110,10 @@ nms_compact_kernel(const float* __restrict__ scores, float* __restrict__ scores_
   __syncthreads();
   int pos = warp_tot[wid] + incl - mine;
   const int P = base_s;
-  if (tid == 0) *count = P;
+  if (tid == 0) {
+    *count = P;                               // true count: the host turns P > max_persons into an error
+    *count_clamped = min(P, max_persons);     // what the per-person kernels may touch
+  }
   for (int i = beg; i < end; ++i) {
     const float v = scores_out[i];
     if (v >= thresh) {
@@ -142,7 +145,7 @@ __global__ void forced_idx_kernel(const float* __restrict__ scores, float* __res
                                   int res, const int64_t* __restrict__ idx4, int P, int* __restrict__ det_b,
                                   int* __restrict__ det_y, int* __restrict__ det_x,
                                   float* __restrict__ det_score, int* __restrict__ count,
-                                  int* __restrict__ img_off) {
+                                  int* __restrict__ count_clamped, int* __restrict__ img_off) {
   const int N = res * res;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * N; i += gridDim.x * blockDim.x)
     scores_out[i] = scores[i];
@@ -153,7 +156,10 @@ __global__ void forced_idx_kernel(const float* __restrict__ scores, float* __res
       det_b[p] = b; det_y[p] = y; det_x[p] = x;
       det_score[p] = scores[b * N + y * res + x];
     }
-    if (threadIdx.x == 0) *count = P;
+    if (threadIdx.x == 0) {
+      *count = P;
+      *count_clamped = P;  // forced_P <= max_persons is checked on the host
+    }
     for (int b = threadIdx.x; b <= B; b += blockDim.x) {
       int c = 0;
       for (int p = 0; p < P; ++p) c += (static_cast<int>(idx4[p]) < b) ? 1 : 0;
@@ -564,19 +570,19 @@ int rowdot_sigmoid(const __half* hid, int64_t ld, const float* w, const float* b
 
 int nms_compact(const float* scores, float* scores_out, int B, int res, int nms_k, float thresh,
                 int max_persons, int* det_b, int* det_y, int* det_x, float* det_score, int* count,
-                int* img_off, cudaStream_t st) {
+                int* count_clamped, int* img_off, cudaStream_t st) {
   MHMR_REQUIRE(nms_k >= 1 && nms_k <= 15, "nms kernel size out of range");
   nms_compact_kernel<<<1, 1024, 0, st>>>(scores, scores_out, B, res, nms_k, thresh, max_persons, det_b,
-                                         det_y, det_x, det_score, count, img_off);
+                                         det_y, det_x, det_score, count, count_clamped, img_off);
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }
 
 int forced_detections(const float* scores, float* scores_out, int B, int res, const int64_t* idx4, int P,
-               int* det_b, int* det_y, int* det_x, float* det_score, int* count, int* img_off,
-               cudaStream_t st) {
+               int* det_b, int* det_y, int* det_x, float* det_score, int* count, int* count_clamped,
+               int* img_off, cudaStream_t st) {
   forced_idx_kernel<<<64, 256, 0, st>>>(scores, scores_out, B, res, idx4, P, det_b, det_y, det_x, det_score,
-                                        count, img_off);
+                                        count, count_clamped, img_off);
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }

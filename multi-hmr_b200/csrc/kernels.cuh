@@ -28,10 +28,10 @@ int rowdot_sigmoid(const __half* hid, int64_t ld, const float* w, const float* b
                    int D, cudaStream_t st);
 int nms_compact(const float* scores, float* scores_out, int B, int res, int nms_k, float thresh,
                 int max_persons, int* det_b, int* det_y, int* det_x, float* det_score, int* count,
-                int* img_off, cudaStream_t st);
+                int* count_clamped, int* img_off, cudaStream_t st);
 int forced_detections(const float* scores, float* scores_out, int B, int res, const int64_t* idx4, int P,
-               int* det_b, int* det_y, int* det_x, float* det_score, int* count, int* img_off,
-               cudaStream_t st);
+               int* det_b, int* det_y, int* det_x, float* det_score, int* count, int* count_clamped,
+               int* img_off, cudaStream_t st);
 int loc_to_transl(const float* loc, const float* dist, const float* K_det, int P, float* transl,
                   cudaStream_t st);
 int invert_K(const float* K, float* Kinv, int B, cudaStream_t st);

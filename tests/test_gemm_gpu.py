@@ -25,7 +25,7 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
-@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("bn", [128, 256, 512])
 def test_gemm_bias_f16(cuda_device, M, N, K, bn):
     from multihmr_b200 import ops
 
@@ -42,8 +42,9 @@ def test_gemm_bias_f16(cuda_device, M, N, K, bn):
     assert err <= 1e-3 * max(scale, 1.0) + 1e-3, (err, scale)
 
 
+@pytest.mark.parametrize("bn", [256, 512])
 @pytest.mark.parametrize("epi", ["gelu", "relu"])
-def test_gemm_act_f16(cuda_device, epi):
+def test_gemm_act_f16(cuda_device, epi, bn):
     from multihmr_b200 import ops
 
     M, N, K = 1537, 4096, 1024
@@ -53,14 +54,15 @@ def test_gemm_act_f16(cuda_device, epi):
     bias = torch.randn(N, generator=g).to(cuda_device)
     out = torch.empty(M, N, device=cuda_device, dtype=torch.float16)
     kind = ops.EPI_BIAS_GELU_F16 if epi == "gelu" else ops.EPI_BIAS_RELU_F16
-    ops.gemm_f16(a, w, kind, out, bias=bias)
+    ops.gemm_f16(a, w, kind, out, bias=bias, block_n=bn)
     pre = _ref_linear(a, w) + bias
     ref = torch.nn.functional.gelu(pre) if epi == "gelu" else torch.relu(pre)
     err = (out.float() - ref).abs().max().item()
     assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), err
 
 
-def test_gemm_layerscale_residual_f32(cuda_device):
+@pytest.mark.parametrize("bn", [256, 512])
+def test_gemm_layerscale_residual_f32(cuda_device, bn):
     from multihmr_b200 import ops
 
     M, N, K = 4097 * 2, 1024, 4096
@@ -71,7 +73,7 @@ def test_gemm_layerscale_residual_f32(cuda_device):
     gamma = torch.rand(N, generator=g).to(cuda_device)
     x0 = torch.randn(M, N, generator=g).to(cuda_device)
     x = x0.clone()
-    ops.gemm_f16(a, w, ops.EPI_LS_RESID_F32, x, bias=bias, gamma=gamma)
+    ops.gemm_f16(a, w, ops.EPI_LS_RESID_F32, x, bias=bias, gamma=gamma, block_n=bn)
     ref = x0 + gamma * (_ref_linear(a, w) + bias)
     err = (x - ref).abs().max().item()
     # fp32 everywhere after the exact fp16 products: only summation-order noise
@@ -97,7 +99,8 @@ def test_gemm_rowadd_remap_f32(cuda_device):
     assert err <= 2e-4, err
 
 
-def test_gemm_bias_f32_nobias(cuda_device):
+@pytest.mark.parametrize("bn", [256, 512])
+def test_gemm_bias_f32_nobias(cuda_device, bn):
     from multihmr_b200 import ops
 
     M, N, K = 2304, 1024, 1152
@@ -105,7 +108,7 @@ def test_gemm_bias_f32_nobias(cuda_device):
     a = torch.randn(M, K, generator=g).to(cuda_device).half()
     w = (torch.randn(N, K, generator=g) * 0.05).to(cuda_device).half()
     out = torch.empty(M, N, device=cuda_device)
-    ops.gemm_f16(a, w, ops.EPI_BIAS_F32, out)
+    ops.gemm_f16(a, w, ops.EPI_BIAS_F32, out, block_n=bn)
     err = (out - _ref_linear(a, w)).abs().max().item()
     assert err <= 2e-4, err
 

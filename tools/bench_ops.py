@@ -32,12 +32,15 @@ def bench_gemm(dev, flush):
     res = []
     for (M, N, K, epi, bn) in [
         (32776, 3072, 1024, ops.EPI_BIAS_F16, 256),
+        (32776, 3072, 1024, ops.EPI_BIAS_F16, 512),
         (32776, 1024, 1024, ops.EPI_LS_RESID_F32, 256),
-        (32776, 1024, 1024, ops.EPI_LS_RESID_F32, 128),
+        (32776, 1024, 1024, ops.EPI_LS_RESID_F32, 512),
         (32776, 4096, 1024, ops.EPI_BIAS_GELU_F16, 256),
+        (32776, 4096, 1024, ops.EPI_BIAS_GELU_F16, 512),
         (32776, 1024, 4096, ops.EPI_LS_RESID_F32, 256),
-        (32776, 1024, 4096, ops.EPI_LS_RESID_F32, 128),
+        (32776, 1024, 4096, ops.EPI_LS_RESID_F32, 512),
         (32768, 1024, 1152, ops.EPI_BIAS_F32, 256),
+        (32768, 1024, 1152, ops.EPI_BIAS_F32, 512),
     ]:
         a = torch.randn(M, K, device=dev).half()
         w = (torch.randn(N, K, device=dev) * 0.03).half()
