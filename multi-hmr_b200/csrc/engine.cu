@@ -138,6 +138,9 @@ namespace {
   const float* var = e->w(key, numel);                  \
   if (var == nullptr) return MHMR_ERR_STATE;
 
+// CTA-pair 256x256 tiles (cta_group::2) whenever N is a multiple of 256, else single-CTA 128x128 tiles
+int pick_bn(int N) { return (N % 256 == 0) ? 512 : 128; }
+
 int to_f16(mhmr_engine* e, const float* src, int64_t lds, int rows, int cols, int64_t ldd, __half** out,
            cudaStream_t st) {
   TRY(e->alloc(out, static_cast<size_t>(rows) * ldd));
@@ -171,7 +174,7 @@ int finalize_vit(mhmr_engine* e, cudaStream_t st) {
 
   GemmEpi ep;
   ep.rowadd = e->rowadd; ep.out = e->X; ep.ldo = D; ep.rows_in = N; ep.rows_out = T; ep.row_off = 1;
-  TRY(gemm_plan_init(&e->patch_plan, e->A16, 592, e->Wpatch, 592, Bm * N, D, 588, EPI_ROWADD_F32, ep, 128));
+  TRY(gemm_plan_init(&e->patch_plan, e->A16, 592, e->Wpatch, 592, Bm * N, D, 588, EPI_ROWADD_F32, ep, pick_bn(D)));
 
   e->vit.resize(e->depth);
   for (int l = 0; l < e->depth; ++l) {
@@ -191,13 +194,13 @@ int finalize_vit(mhmr_engine* e, cudaStream_t st) {
     TRY(to_f16(e, wfc1, D, 4 * D, D, D, &L.Wfc1, st));
     TRY(to_f16(e, wfc2, 4 * D, D, 4 * D, 4 * D, &L.Wfc2, st));
     GemmEpi a; a.bias = bqkv; a.out = e->QKV16; a.ldo = 3 * D;
-    TRY(gemm_plan_init(&L.qkv, e->Xn16, D, L.Wqkv, D, static_cast<int>(M), 3 * D, D, EPI_BIAS_F16, a, 256));
+    TRY(gemm_plan_init(&L.qkv, e->Xn16, D, L.Wqkv, D, static_cast<int>(M), 3 * D, D, EPI_BIAS_F16, a, pick_bn(3 * D)));
     GemmEpi p; p.bias = bproj; p.gamma = ls1; p.out = e->X; p.ldo = D;
-    TRY(gemm_plan_init(&L.proj, e->O16, D, L.Wproj, D, static_cast<int>(M), D, D, EPI_LS_RESID_F32, p, 256));
+    TRY(gemm_plan_init(&L.proj, e->O16, D, L.Wproj, D, static_cast<int>(M), D, D, EPI_LS_RESID_F32, p, pick_bn(D)));
     GemmEpi f1; f1.bias = bfc1; f1.out = e->H16; f1.ldo = 4 * D;
-    TRY(gemm_plan_init(&L.fc1, e->Xn16, D, L.Wfc1, D, static_cast<int>(M), 4 * D, D, EPI_BIAS_GELU_F16, f1, 256));
+    TRY(gemm_plan_init(&L.fc1, e->Xn16, D, L.Wfc1, D, static_cast<int>(M), 4 * D, D, EPI_BIAS_GELU_F16, f1, pick_bn(4 * D)));
     GemmEpi f2; f2.bias = bfc2; f2.gamma = ls2; f2.out = e->X; f2.ldo = D;
-    TRY(gemm_plan_init(&L.fc2, e->H16, 4 * D, L.Wfc2, 4 * D, static_cast<int>(M), D, 4 * D, EPI_LS_RESID_F32, f2, 256));
+    TRY(gemm_plan_init(&L.fc2, e->H16, 4 * D, L.Wfc2, 4 * D, static_cast<int>(M), D, 4 * D, EPI_LS_RESID_F32, f2, pick_bn(D)));
   }
   if (e->w(enc + "norm.weight", D) == nullptr || e->w(enc + "norm.bias", D) == nullptr) return MHMR_ERR_STATE;
   return MHMR_OK;
@@ -227,7 +230,7 @@ int finalize_head(mhmr_engine* e, cudaStream_t st) {
   (void)c2w; (void)c2b;
   TRY(to_f16(e, c0w, D, D, D, D, &e->Wcls0, st));
   GemmEpi ce; ce.bias = c0b; ce.out = e->H16; ce.ldo = D;
-  TRY(gemm_plan_init(&e->cls0_plan, e->ctx16, Cp, e->Wcls0, D, static_cast<int>(BN), D, D, EPI_BIAS_RELU_F16, ce, 256));
+  TRY(gemm_plan_init(&e->cls0_plan, e->ctx16, Cp, e->Wcls0, D, static_cast<int>(BN), D, D, EPI_BIAS_RELU_F16, ce, pick_bn(D)));
   NEEDW(o0w, "mlp_offset.0.weight", static_cast<int64_t>(D) * D) NEEDW(o0b, "mlp_offset.0.bias", D)
   NEEDW(o2w, "mlp_offset.2.weight", 2ll * D) NEEDW(o2b, "mlp_offset.2.bias", 2)
   (void)o0w; (void)o0b; (void)o2w; (void)o2b;
@@ -283,7 +286,7 @@ int finalize_head(mhmr_engine* e, cudaStream_t st) {
   TRY(e->alloc(&e->Wkv16, static_cast<size_t>(e->nkv) * Cp));
   TRY(f32_to_f16_2d(e->Wkv32, Cq, e->Wkv16, Cp, e->nkv, C, st));  // cols >= C stay zero
   GemmEpi ke; ke.out = e->KV32; ke.ldo = e->nkv;
-  TRY(gemm_plan_init(&e->kv_plan, e->ctx16, Cp, e->Wkv16, Cp, static_cast<int>(BN), e->nkv, Cp, EPI_BIAS_F32, ke, 256));
+  TRY(gemm_plan_init(&e->kv_plan, e->ctx16, Cp, e->Wkv16, Cp, static_cast<int>(BN), e->nkv, Cp, EPI_BIAS_F32, ke, pick_bn(e->nkv)));
 
   // decoders stacked: [pose6 318 | betas nb | cam 3 | expression 10], bias + init (model.py:571-575)
   e->ndec = 318 + nb + 3 + 10;

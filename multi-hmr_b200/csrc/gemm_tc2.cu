@@ -45,7 +45,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 // Arrive on the barrier at the same smem offset in the leader CTA (rank 0) of the pair.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   const uint32_t addr = smem_u32(bar) & kPeerBitMask;
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
                                                 int32_t c_inner, int32_t c_outer) {
