@@ -350,7 +350,14 @@ int finalize_body(mhmr_engine* e, cudaStream_t st) {
   TRY(smplx_fold_jreg(jr, vt, V, 3, Jt, st));
   TRY(e->alloc(&Jd, static_cast<size_t>(55) * 3 * L));
   TRY(smplx_fold_jreg(jr, sfull, V, 3 * L, Jd, st));
-  bm.PDX = PDX; bm.vt = vtp; bm.lbs_weights = lw; bm.Jt = Jt; bm.Jdirs = Jd;
+  // skinning weights padded to whole 72-vertex tiles (the vertex kernel bulk-copies one tile per CTA)
+  const int tv = smplx_tile_verts();
+  const int Vpad = (V + tv - 1) / tv * tv;
+  float* lwp = nullptr;
+  TRY(e->alloc(&lwp, static_cast<size_t>(Vpad) * 55));
+  MHMR_CUDA_CHECK(cudaMemcpyAsync(lwp, lw, 55ll * V * 4, cudaMemcpyDeviceToDevice, st));
+  bm.PDX = PDX; bm.vt = vtp; bm.lbs_weights_padded = lwp; bm.Jt = Jt; bm.Jdirs = Jd;
+  TRY(smplx_make_tmap(&bm));
   bm.parents = parents; bm.extra_idx = extra; bm.lmk_tri = tri; bm.lmk_bary = bary;
   TRY(e->alloc(&e->sx.cf, static_cast<size_t>(Pm) * (486 + L)));
   TRY(e->alloc(&e->sx.Amat, static_cast<size_t>(Pm) * 55 * 12));

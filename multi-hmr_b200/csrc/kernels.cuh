@@ -65,7 +65,8 @@ struct SmplxDeviceModel {
   int ldp = 0;          // PDX / vt row pitch: 3V rounded up to 4
   const float* PDX = nullptr;          // [486 + L, ldp]
   const float* vt = nullptr;           // [ldp] v_template flattened
-  const float* lbs_weights = nullptr;  // [V, 55]
+  const float* lbs_weights_padded = nullptr;  // [ceil(V/72)*72, 55], zero rows beyond V
+  CUtensorMap tmPDX;                   // TMA descriptor of PDX (boxes of 16 rows x 220 columns)
   const float* Jt = nullptr;           // [55, 3]   J_regressor . v_template
   const float* Jdirs = nullptr;        // [55*3, L] J_regressor . shapedirs
   const int* parents = nullptr;        // [55]
@@ -79,6 +80,8 @@ struct SmplxScratch {
   float* xf = nullptr;      // [max_persons, 16]
   float* jposed = nullptr;  // [max_persons, 55, 3]
 };
+int smplx_make_tmap(SmplxDeviceModel* bm);
+int smplx_tile_verts();
 int smplx_build_pdx(const float* posedirs, const float* sdirs_full, int L, int V, int ldp, float* PDX,
                     cudaStream_t st);
 int smplx_fold_jreg(const float* Jr, const float* M, int V, int Q, float* out, cudaStream_t st);

@@ -8,9 +8,9 @@
 //     coefficient vector cf[p] = [pose_feature(486) | betas | expression].
 //   * J_regressor is folded at load time: J(beta) = Jt + Jdirs . beta  (J is linear in beta), which removes
 //     a 2.3 MB read and a cross-CTA reduction.
-//   * one CTA per SM (72 vertices = 216 columns per CTA for V = 10475 on 148 SMs), 8 k-slices per column
-//     group so that every SM keeps ~40 KB of float4 loads in flight; all persons of a block of 8 are
-//     accumulated per streamed row (the matrix is read from HBM once; further person blocks hit L2).
+//   * one CTA per SM (72 vertices = 216 columns per CTA for V = 10475 on 148 SMs); the CTA's column slab
+//     is streamed through a TMA-fed shared-memory ring and 16 persons are accumulated per streamed row
+//     (the matrix is read from HBM once; further blocks of 16 persons re-stream it from L2).
 #include "kernels.cuh"
 
 namespace mhmr {
@@ -172,20 +172,31 @@ smplx_prep_kernel(const float* __restrict__ rotvec, const float* __restrict__ sh
 
 // ------------------------------------------------------------------------------------------------
 // Vertex kernel: v_posed = v_template + cf . PDX ; skinning ; root placement ; optional projection.
-//   thread = (column group of 4 coordinates, k-slice): the 8 k-slices of a column group are 8 adjacent lanes,
-//   slice s streams rows k = s, s+8, ... with 8 independent 128-bit loads in flight, 16 persons are
-//   accumulated per streamed row, and the slices are folded with warp shuffles (no smem round trip).
+// One CTA per SM (72 vertices = 216 coordinate columns).  A producer warp streams this CTA's column slab
+// of PDX through a 6-stage shared-memory ring with TMA (16 rows x 220 columns per box; the 220-float pitch
+// makes the consumers' 128-bit reads conflict-free) and bulk-copies the skinning-weight tile; 432 consumer
+// threads = 54 column groups x 8 row lanes accumulate 16 persons per streamed row, so the 64 MB matrix
+// is read from HBM exactly once per forward with ~80 KB in flight per SM, decoupled from the FMA work.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTV = 72;          // vertices per CTA
-constexpr int kTC = kTV * 3;     // 216 columns
-constexpr int kCG = kTC / 4;     // 54 float4 column groups
-constexpr int kKS = 8;           // k-slices = adjacent lanes
-constexpr int kPB = 16;          // persons per pass
-constexpr int kVertThreads = kCG * kKS;  // 432
-constexpr int kKTMax = 512;      // >= 486 + 21
+constexpr int kTV = 72;            // vertices per CTA
+constexpr int kTC = kTV * 3;       // 216 columns
+constexpr int kCG = kTC / 4;       // 54 float4 column groups
+constexpr int kRL = 8;             // row lanes (adjacent lanes of a warp)
+constexpr int kChunkRows = 16;     // PDX rows per TMA box
+constexpr int kPitch = 220;        // floats per staged row (box inner size; 880 B)
+constexpr int kStagesV = 6;
+constexpr int kPB = 16;            // persons per pass
+constexpr int kConsumers = kCG * kRL;              // 432
+constexpr int kConsumerWarps = (kConsumers + 31) / 32;  // 14
+constexpr int kVertThreads = kConsumerWarps * 32 + 32;  // + producer warp = 480
+constexpr int kKTMax = 512;        // >= 486 + 21, multiple of kChunkRows
+constexpr int kCfPitch = 20;       // floats per coefficient row (16 persons + pad: conflict-free)
+constexpr int kStageFloats = kChunkRows * kPitch;
 
 struct VertSmem {
-  float pfs[kKTMax][kPB];
+  float stage[kStagesV][kStageFloats];   // 6 x 14080 B (TMA destinations: 128-byte aligned)
+  float Ws[kTV][kNJ];                    // skinning-weight tile (bulk copy destination, 16-byte aligned)
+  float pfs[kKTMax][kCfPitch];
   float As[kPB][kNJ * 12];
   float xf[kPB][16];
   float tr[kPB][4];
@@ -193,141 +204,178 @@ struct VertSmem {
   float vps[kPB][kTC];
   float outs[kPB][kTC];
   float outs2[kPB][kTV * 2];
-  float Ws[kTV][kNJ];
+  uint64_t full_bar[kStagesV];
+  uint64_t empty_bar[kStagesV];
+  uint64_t w_bar;
 };
 
-__device__ __forceinline__ float4 ldg_stream(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
-
 __global__ void __launch_bounds__(kVertThreads, 1)
-smplx_vertex_kernel(const float* __restrict__ PDX, int ldp, int KT, const float* __restrict__ vt,
-                    const float* __restrict__ Wl, const float* __restrict__ cf,
+smplx_vertex_kernel(const __grid_constant__ CUtensorMap tmPDX, int KT, const float* __restrict__ vt,
+                    const float* __restrict__ Wl_padded, const float* __restrict__ cf,
                     const float* __restrict__ Amat, const float* __restrict__ xf,
                     const float* __restrict__ transl, const float* __restrict__ K_det,
                     const int* __restrict__ count, int V, float* __restrict__ v3d,
                     float* __restrict__ v2d) {
   extern __shared__ uint8_t vsmem_raw[];
-  VertSmem& sm = *reinterpret_cast<VertSmem*>(vsmem_raw);
+  VertSmem& sm = *reinterpret_cast<VertSmem*>((reinterpret_cast<uintptr_t>(vsmem_raw) + 127) & ~static_cast<uintptr_t>(127));
   const int P = *count;
   if (P <= 0) return;
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   const int v0 = blockIdx.x * kTV;
   const int col0 = v0 * 3;
   const int nv = min(kTV, V - v0);
   const int ncol = nv * 3;
-  const int cg = tid >> 3, slice = tid & 7;
-  const bool col_ok = (col0 + cg * 4) < ldp;
-  const int n_iter = (KT + kKS - 1) / kKS;
+  const int n_chunks = (KT + kChunkRows - 1) / kChunkRows;
+  const int n_pass = (P + kPB - 1) / kPB;
+  const bool is_producer = (warp == kConsumerWarps);
 
-  for (int i = tid; i < kTV * kNJ; i += kVertThreads) {
-    const int v = i / kNJ, jj = i - v * kNJ;
-    sm.Ws[v][jj] = (v < nv) ? Wl[static_cast<int64_t>(v0 + v) * kNJ + jj] : 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < kStagesV; ++s) {
+      mbar_init(&sm.full_bar[s], 1);
+      mbar_init(&sm.empty_bar[s], kConsumerWarps);
+    }
+    mbar_init(&sm.w_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (is_producer) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmPDX);
+      // skinning-weight tile: rows v0..v0+71 of the padded [ceil(V/72)*72, 55] matrix are contiguous
+      mbar_arrive_expect_tx(&sm.w_bar, kTV * kNJ * 4);
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(&sm.Ws[0][0])),
+          "l"(Wl_padded + static_cast<int64_t>(v0) * kNJ), "r"(kTV * kNJ * 4), "r"(smem_u32(&sm.w_bar))
+          : "memory");
+      // fill the ring right away: the first kStagesV boxes need no hand-shake, so the HBM stream starts
+      // while the other warps are still staging the per-person coefficients
+      for (int c = 0; c < min(kStagesV, n_chunks); ++c) {
+        mbar_arrive_expect_tx(&sm.full_bar[c], kStageFloats * 4);
+        tma_load_2d_hint(&sm.stage[c][0], &tmPDX, &sm.full_bar[c], col0, c * kChunkRows,
+                         n_pass > 1 ? kCacheEvictLast : kCacheEvictFirst);
+      }
+    }
   }
 
-  for (int pb0 = 0; pb0 < P; pb0 += kPB) {
+  const int ctid = min(tid, kConsumers - 1);  // idle lanes of the last consumer warp shadow a real thread
+  const bool active = !is_producer && tid < kConsumers;
+  const int cg = ctid >> 3, r = ctid & 7;
+  uint32_t it = 0;
+
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int pb0 = pass * kPB;
     const int np = min(kPB, P - pb0);
-    __syncthreads();  // previous pass finished with all buffers
-    for (int i = tid; i < KT * kPB; i += kVertThreads) {
+    __syncthreads();  // previous pass finished with the per-person buffers
+    for (int i = tid; i < kKTMax * kPB; i += kVertThreads) {
       const int k = i / kPB, j = i - k * kPB;
-      sm.pfs[k][j] = (j < np) ? cf[static_cast<int64_t>(pb0 + j) * KT + k] : 0.f;
+      sm.pfs[k][j] = (j < np && k < KT) ? cf[static_cast<int64_t>(pb0 + j) * KT + k] : 0.f;
     }
     for (int i = tid; i < kPB * kNJ * 12; i += kVertThreads) {
-      const int j = i / (kNJ * 12), r = i - j * (kNJ * 12);
-      sm.As[j][r] = (j < np) ? Amat[static_cast<int64_t>(pb0 + j) * kNJ * 12 + r] : 0.f;
+      const int j = i / (kNJ * 12), q = i - j * (kNJ * 12);
+      sm.As[j][q] = (j < np) ? Amat[static_cast<int64_t>(pb0 + j) * kNJ * 12 + q] : 0.f;
     }
     for (int i = tid; i < kPB * 16; i += kVertThreads) {
-      const int j = i >> 4, r = i & 15;
-      sm.xf[j][r] = (j < np) ? xf[static_cast<int64_t>(pb0 + j) * 16 + r] : 0.f;
-      if (r < 4) sm.tr[j][r] = (j < np && r < 3) ? transl[(pb0 + j) * 3 + r] : 0.f;
-      if (r < 9) sm.Kd[j][r] = (j < np) ? K_det[(pb0 + j) * 9 + r] : 0.f;
+      const int j = i >> 4, q = i & 15;
+      sm.xf[j][q] = (j < np) ? xf[static_cast<int64_t>(pb0 + j) * 16 + q] : 0.f;
+      if (q < 4) sm.tr[j][q] = (j < np && q < 3) ? transl[(pb0 + j) * 3 + q] : 0.f;
+      if (q < 9) sm.Kd[j][q] = (j < np) ? K_det[(pb0 + j) * 9 + q] : 0.f;
     }
     __syncthreads();
 
-    // ---- stream the PDX tile: acc[i][j] += cf[j][k] * PDX[k][col + i], rows k = slice, slice+8, ...
-    float acc[4][kPB];
+    if (!is_producer) {
+      // ---- consume the streamed rows: acc[i][j] += cf[j][k] * PDX[k][col + i]
+      float acc[4][kPB];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < kPB; ++j) acc[i][j] = 0.f;
-    if (col_ok) {
-      const float* src = PDX + col0 + cg * 4;
-#pragma unroll 1
-      for (int it0 = 0; it0 < n_iter; it0 += 8) {
-        float4 w[8];
+        for (int j = 0; j < kPB; ++j) acc[i][j] = 0.f;
+      for (int c = 0; c < n_chunks; ++c, ++it) {
+        const uint32_t s = it % kStagesV, ph = (it / kStagesV) & 1u;
+        mbar_wait(&sm.full_bar[s], ph);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int k = (it0 + u) * kKS + slice;
-          w[u] = (k < KT) ? ldg_stream(src + static_cast<int64_t>(k) * ldp) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int k = min((it0 + u) * kKS + slice, KT - 1);  // w is zero when k is out of range
+        for (int h = 0; h < kChunkRows / kRL; ++h) {
+          const int row = h * kRL + r;
+          const int k = c * kChunkRows + row;  // rows >= KT are zero-filled by TMA, pfs rows are zero
+          const float4 w = *reinterpret_cast<const float4*>(&sm.stage[s][row * kPitch + cg * 4]);
 #pragma unroll
           for (int q = 0; q < kPB / 4; ++q) {
-            const float4 c = *reinterpret_cast<const float4*>(&sm.pfs[k][q * 4]);
-            const float cj[4] = {c.x, c.y, c.z, c.w};
+            const float4 cc = *reinterpret_cast<const float4*>(&sm.pfs[k][q * 4]);
+            const float cj[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              acc[0][q * 4 + j] = fmaf(cj[j], w[u].x, acc[0][q * 4 + j]);
-              acc[1][q * 4 + j] = fmaf(cj[j], w[u].y, acc[1][q * 4 + j]);
-              acc[2][q * 4 + j] = fmaf(cj[j], w[u].z, acc[2][q * 4 + j]);
-              acc[3][q * 4 + j] = fmaf(cj[j], w[u].w, acc[3][q * 4 + j]);
+              acc[0][q * 4 + j] = fmaf(cj[j], w.x, acc[0][q * 4 + j]);
+              acc[1][q * 4 + j] = fmaf(cj[j], w.y, acc[1][q * 4 + j]);
+              acc[2][q * 4 + j] = fmaf(cj[j], w.z, acc[2][q * 4 + j]);
+              acc[3][q * 4 + j] = fmaf(cj[j], w.w, acc[3][q * 4 + j]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty_bar[s]);
+      }
+      // ---- fold the 8 row lanes (adjacent lanes), add the template; lane r keeps persons 2r, 2r+1
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < kPB; ++j) {
+          float v = acc[i][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          acc[i][j] = v;
+        }
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < kPB; ++j) {
+          if ((j >> 1) == r) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int cc = cg * 4 + i;
+              sm.vps[j][cc] = (cc < ncol) ? (vt[col0 + cc] + acc[i][j]) : 0.f;
             }
           }
         }
       }
-    }
-    // ---- fold the 8 k-slices (adjacent lanes), add the template; lane s keeps persons 2s, 2s+1
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < kPB; ++j) {
-        float v = acc[i][j];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        acc[i][j] = v;
-      }
-#pragma unroll
-    for (int j = 0; j < kPB; ++j) {
-      if ((j >> 1) == slice) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = cg * 4 + i;
-          sm.vps[j][c] = (c < ncol) ? (vt[col0 + c] + acc[i][j]) : 0.f;
-        }
+    } else if (lane == 0) {
+      // ---- producer: stream this CTA's column slab, 16 rows per box, through the ring
+      for (int c = 0; c < n_chunks; ++c, ++it) {
+        if (pass == 0 && c < kStagesV) continue;  // already in flight (prologue)
+        const uint32_t s = it % kStagesV, ph = (it / kStagesV) & 1u;
+        mbar_wait(&sm.empty_bar[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&sm.full_bar[s], kStageFloats * 4);
+        tma_load_2d_hint(&sm.stage[s][0], &tmPDX, &sm.full_bar[s], col0, c * kChunkRows,
+                         n_pass > 1 ? kCacheEvictLast : kCacheEvictFirst);
       }
     }
+    if (pass == 0) mbar_wait(&sm.w_bar, 0);  // skinning weights have landed
     __syncthreads();
 
     // ---- skinning + root placement + projection, one (vertex, person) pair per thread-iteration
     for (int i = tid; i < kTV * kPB; i += kVertThreads) {
       const int j = i / kTV, v = i - j * kTV;
       if (v >= nv || j >= np) continue;
-      float T[12];
-#pragma unroll
-      for (int r = 0; r < 12; ++r) T[r] = 0.f;
+      float4 T0 = make_float4(0.f, 0.f, 0.f, 0.f), T1 = T0, T2 = T0;
       for (int jj = 0; jj < kNJ; ++jj) {
         const float w = sm.Ws[v][jj];
-        const float* A = &sm.As[j][jj * 12];
-#pragma unroll
-        for (int r = 0; r < 12; ++r) T[r] = fmaf(w, A[r], T[r]);
+        const float4* A = reinterpret_cast<const float4*>(&sm.As[j][jj * 12]);
+        const float4 a0 = A[0], a1 = A[1], a2 = A[2];
+        T0.x = fmaf(w, a0.x, T0.x); T0.y = fmaf(w, a0.y, T0.y); T0.z = fmaf(w, a0.z, T0.z); T0.w = fmaf(w, a0.w, T0.w);
+        T1.x = fmaf(w, a1.x, T1.x); T1.y = fmaf(w, a1.y, T1.y); T1.z = fmaf(w, a1.z, T1.z); T1.w = fmaf(w, a1.w, T1.w);
+        T2.x = fmaf(w, a2.x, T2.x); T2.y = fmaf(w, a2.y, T2.y); T2.z = fmaf(w, a2.z, T2.z); T2.w = fmaf(w, a2.w, T2.w);
       }
       const float x = sm.vps[j][v * 3], y = sm.vps[j][v * 3 + 1], z = sm.vps[j][v * 3 + 2];
-      float q[3];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) q[r] = T[r * 4] * x + T[r * 4 + 1] * y + T[r * 4 + 2] * z + T[r * 4 + 3];
+      const float q0 = T0.x * x + T0.y * y + T0.z * z + T0.w;
+      const float q1 = T1.x * x + T1.y * y + T1.z * z + T1.w;
+      const float q2 = T2.x * x + T2.y * y + T2.z * z + T2.w;
       const float* X = sm.xf[j];
-      const float dx = q[0] - X[9], dy = q[1] - X[10], dz = q[2] - X[11];
+      const float dx = q0 - X[9], dy = q1 - X[10], dz = q2 - X[11];
       float o[3];
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
-        o[r] = ((X[r * 3] * dx + X[r * 3 + 1] * dy + X[r * 3 + 2] * dz) - X[12 + r]) + sm.tr[j][r];
+      for (int q = 0; q < 3; ++q)
+        o[q] = ((X[q * 3] * dx + X[q * 3 + 1] * dy + X[q * 3 + 2] * dz) - X[12 + q]) + sm.tr[j][q];
       sm.outs[j][v * 3] = o[0];
       sm.outs[j][v * 3 + 1] = o[1];
       sm.outs[j][v * 3 + 2] = o[2];
@@ -434,6 +482,13 @@ __global__ void fold_jreg_kernel(const float* __restrict__ Jr, const float* __re
 
 }  // namespace
 
+// TMA descriptor of PDX [KT, ldp] fp32: boxes of 16 rows x 220 columns, no swizzle.
+int smplx_make_tmap(SmplxDeviceModel* bm) {
+  return make_tmap_2d(&bm->tmPDX, bm->PDX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kPoseFeat + bm->L, bm->ldp,
+                      static_cast<uint64_t>(bm->ldp) * 4, kChunkRows, kPitch, false);
+}
+int smplx_tile_verts() { return kTV; }
+
 int smplx_build_pdx(const float* posedirs, const float* sdirs_full, int L, int V, int ldp, float* PDX,
                     cudaStream_t st) {
   build_pdx_kernel<<<dim3(32, kPoseFeat + L), 256, 0, st>>>(posedirs, sdirs_full, L, V * 3, ldp, PDX);
@@ -458,14 +513,14 @@ int smplx_forward(const SmplxDeviceModel& bm, const float* rotvec, const float* 
                                                 ws.xf, ws.jposed);
   MHMR_CUDA_CHECK(cudaGetLastError());
   static bool attr_set = false;
+  const int vsmem = static_cast<int>(sizeof(VertSmem)) + 128;
   if (!attr_set) {
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(smplx_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(VertSmem))));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(smplx_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vsmem));
     attr_set = true;
   }
   const int tiles = (bm.V + kTV - 1) / kTV;
-  smplx_vertex_kernel<<<tiles, kVertThreads, sizeof(VertSmem), st>>>(
-      bm.PDX, bm.ldp, KT, bm.vt, bm.lbs_weights, ws.cf, ws.Amat, ws.xf, transl, K_det, count, bm.V, v3d, v2d);
+  smplx_vertex_kernel<<<tiles, kVertThreads, vsmem, st>>>(bm.tmPDX, KT, bm.vt, bm.lbs_weights_padded, ws.cf, ws.Amat,
+                                                         ws.xf, transl, K_det, count, bm.V, v3d, v2d);
   MHMR_CUDA_CHECK(cudaGetLastError());
   smplx_joints_kernel<<<max_persons, 128, 0, st>>>(ws.jposed, ws.xf, transl, K_det, v3d, bm.extra_idx,
                                                    bm.lmk_tri, bm.lmk_bary, count, bm.V, j3d, j2d,
