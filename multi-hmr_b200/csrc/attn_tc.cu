@@ -69,8 +69,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
                 int T, int D, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment (128B swizzle atoms) by POINTER arithmetic, so that the compiler keeps the
+  // shared address space (a round trip through uintptr_t degrades every access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTileBytes;                     // [kStagesKV]
   uint8_t* sV = smem + kTileBytes * (1 + kStagesKV);   // [kStagesKV]

@@ -40,8 +40,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int kStages = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment (128B swizzle atoms) by POINTER arithmetic, so that the compiler keeps the
+  // shared address space (a round trip through uintptr_t degrades every access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* scratch_base = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + kEpiWarps * kScratchBytes);
   uint64_t* full_bar = bars;                  // [kStages]  TMA -> MMA

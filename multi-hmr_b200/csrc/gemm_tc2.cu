@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(kThreads2, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 int M, int N, int K, GemmEpi ep) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment (128B swizzle atoms) by POINTER arithmetic, so that the compiler keeps the
+  // shared address space (a round trip through uintptr_t degrades every access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* scratch_base = reinterpret_cast<float*>(smem + kStages2 * kStageBytes2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes2 + kEpiWarps2 * kScratchBytes);
   uint64_t* full_bar = bars;                   // [kStages2]  used in the leader: both CTAs' TMA -> MMA

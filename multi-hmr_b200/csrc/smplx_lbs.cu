@@ -217,7 +217,8 @@ smplx_vertex_kernel(const __grid_constant__ CUtensorMap tmPDX, int KT, const flo
                     const int* __restrict__ count, int V, float* __restrict__ v3d,
                     float* __restrict__ v2d) {
   extern __shared__ uint8_t vsmem_raw[];
-  VertSmem& sm = *reinterpret_cast<VertSmem*>((reinterpret_cast<uintptr_t>(vsmem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  // 128-byte alignment by pointer arithmetic (keeps the shared address space: LDS/STS, not generic LD/ST)
+  VertSmem& sm = *reinterpret_cast<VertSmem*>(vsmem_raw + ((128u - (smem_u32(vsmem_raw) & 127u)) & 127u));
   const int P = *count;
   if (P <= 0) return;
   const int tid = threadIdx.x;
