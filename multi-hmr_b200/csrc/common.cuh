@@ -310,6 +310,29 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// Two erf-GELUs at once on the packed f32x2 pipes (same Abramowitz-Stegun form as gelu_erf_fast): the
+// fc1 epilogue is issue-bound, and the packed form halves its floating-point instruction count.
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 z = __fmul2_rn(ax, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  const float2 d = __ffma2_rn(z, make_float2(0.3275911f, 0.3275911f), make_float2(1.0f, 1.0f));
+  float2 t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+  const float2 a = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+  float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+  const float2 pte = __fmul2_rn(__fmul2_rn(p, t), e);
+  const float2 erf_abs = __ffma2_rn(pte, make_float2(-1.0f, -1.0f), make_float2(1.0f, 1.0f));
+  const float2 s = make_float2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, s, hx);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

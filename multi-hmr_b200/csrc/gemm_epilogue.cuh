@@ -35,13 +35,16 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
       const int m = m_base + rl;
       const float4 v0 = *reinterpret_cast<const float4*>(scratch + rl * kScratchStride + cg * 8);
       const float4 v1 = *reinterpret_cast<const float4*>(scratch + rl * kScratchStride + cg * 8 + 4);
-      float x[8] = {v0.x + b0.x, v0.y + b0.y, v0.z + b0.z, v0.w + b0.w,
-                    v1.x + b1.x, v1.y + b1.y, v1.z + b1.z, v1.w + b1.w};
+      float2 y[4] = {__fadd2_rn(make_float2(v0.x, v0.y), make_float2(b0.x, b0.y)),
+                     __fadd2_rn(make_float2(v0.z, v0.w), make_float2(b0.z, b0.w)),
+                     __fadd2_rn(make_float2(v1.x, v1.y), make_float2(b1.x, b1.y)),
+                     __fadd2_rn(make_float2(v1.z, v1.w), make_float2(b1.z, b1.w))};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if constexpr (EPI == EPI_BIAS_GELU_F16) x[i] = gelu_erf_fast(x[i]);
-        if constexpr (EPI == EPI_BIAS_RELU_F16) x[i] = fmaxf(x[i], 0.0f);
+      for (int i = 0; i < 4; ++i) {
+        if constexpr (EPI == EPI_BIAS_GELU_F16) y[i] = gelu_erf_fast2(y[i]);
+        if constexpr (EPI == EPI_BIAS_RELU_F16) y[i] = make_float2(fmaxf(y[i].x, 0.0f), fmaxf(y[i].y, 0.0f));
       }
+      const float x[8] = {y[0].x, y[0].y, y[1].x, y[1].y, y[2].x, y[2].y, y[3].x, y[3].y};
       const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
       const __half2 h2 = __floats2half2_rn(x[4], x[5]), h3 = __floats2half2_rn(x[6], x[7]);
       uint4 pk;
