@@ -183,8 +183,11 @@ def make_images(batch: int, img_size: int, seed: int = 0) -> torch.Tensor:
     return torch.randn(batch, 3, img_size, img_size, generator=g).clamp_(-2.1, 2.6)
 
 
-def make_cameras(batch: int, img_size: int, fov_deg=60.0, jitter: bool = False, seed: int = 0) -> torch.Tensor:
-    """K [B,3,3] as demo.py:get_camera_parameters (demo.py:53-68); optional per-image fov jitter."""
+def make_cameras(batch: int, img_size: int, fov_deg=60.0, jitter: bool = False, seed: int = 0,
+                 asymmetric: bool = False) -> torch.Tensor:
+    """K [B,3,3] as demo.py:get_camera_parameters (demo.py:53-68); optional per-image fov jitter;
+    `asymmetric` adds fx != fy and an off-centre principal point with cx != cy (exercises the (row, col)
+    ordering of model.py:164-178)."""
     g = _gen(seed + 404)
     K = torch.eye(3).repeat(batch, 1, 1)
     for b in range(batch):
@@ -192,6 +195,10 @@ def make_cameras(batch: int, img_size: int, fov_deg=60.0, jitter: bool = False, 
         f = img_size / (2 * math.tan(math.radians(fov) / 2))
         K[b, 0, 0] = K[b, 1, 1] = f
         K[b, 0, 2] = K[b, 1, 2] = img_size // 2
+        if asymmetric:
+            K[b, 1, 1] = f * (0.9 + 0.05 * b)
+            K[b, 0, 2] = img_size * (0.40 + 0.03 * b)
+            K[b, 1, 2] = img_size * (0.57 - 0.02 * b)
     return K
 
 

@@ -35,6 +35,8 @@ CASES = {
                            det_bias=-2.1),
     "s_448_B_forced": dict(backbone="dinov2_vitb14", img_size=448, batch=2, persons=[3, 1], seed=3,
                            jitter=True),
+    "s_224_S_asymK": dict(backbone="dinov2_vits14", img_size=224, batch=2, persons=[2, 2], seed=4, jitter=True,
+                          asymmetric=True),
 }
 
 _CURRENT_BM = {}
@@ -100,7 +102,8 @@ def run_case(name, case, out_dir):
     bm = synth.make_body_model(seed)
     mean = synth.make_mean_params(seed)
     x = synth.make_images(case["batch"], case["img_size"], seed)
-    K = synth.make_cameras(case["batch"], case["img_size"], jitter=case.get("jitter", False), seed=seed)
+    K = synth.make_cameras(case["batch"], case["img_size"], jitter=case.get("jitter", False), seed=seed,
+                           asymmetric=case.get("asymmetric", False))
     res = case["img_size"] // 14
     cfg = multihmr_ref.RefConfig(backbone=case["backbone"], img_size=case["img_size"])
     body = smplx_ref.SMPLXShim(bm, 10)

@@ -14,6 +14,8 @@ CASES = {
     "s_224_S_forced": dict(backbone="dinov2_vits14", img_size=224, batch=3, persons=[2, 0, 3], seed=1),
     "s_224_S_detect": dict(backbone="dinov2_vits14", img_size=224, batch=2, persons=None, seed=2, det_bias=-2.1),
     "s_448_B_forced": dict(backbone="dinov2_vitb14", img_size=448, batch=2, persons=[3, 1], seed=3, jitter=True),
+    "s_224_S_asymK": dict(backbone="dinov2_vits14", img_size=224, batch=2, persons=[2, 2], seed=4, jitter=True,
+                          asymmetric=True),
 }
 
 # Absolute tolerances vs the fp32 reference (BASELINE.json north_star: 1e-3 abs on scores / SMPL-X
@@ -39,7 +41,8 @@ def build_inputs(name):
     sd = synth.make_state_dict(case["backbone"], case["img_size"], seed=seed, det_bias=case.get("det_bias", -4.0))
     bm = synth.make_body_model(seed)
     x = synth.make_images(case["batch"], case["img_size"], seed)
-    K = synth.make_cameras(case["batch"], case["img_size"], jitter=case.get("jitter", False), seed=seed)
+    K = synth.make_cameras(case["batch"], case["img_size"], jitter=case.get("jitter", False), seed=seed,
+                           asymmetric=case.get("asymmetric", False))
     idx = None
     if case["persons"] is not None:
         idx = synth.make_forced_idx(case["batch"], case["img_size"] // 14, case["persons"], seed)

@@ -9,7 +9,7 @@ import parity_util as pu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["s_224_S_forced", "s_448_B_forced", "c1_672_S_forced"])
+@pytest.mark.parametrize("name", ["s_224_S_forced", "s_448_B_forced", "c1_672_S_forced", "s_224_S_asymK"])
 def test_forced_idx_matches_reference(cuda_device, name):
     case, sd, bm, x, K, idx = pu.build_inputs(name)
     gold = pu.load_golden(name)
@@ -97,3 +97,52 @@ def test_batch_invariance_and_smaller_batches(cuda_device):
         one = m(x[b:b + 1], idx=sub, K=K[b:b + 1], is_training=True)
         for k in ("v3d", "rotmat", "shape", "dist", "loc"):
             assert (one[k] - full[k][sel.to(full[k].device)]).abs().max().item() <= 1e-4, k
+
+
+def _oracle_cpu(sd, bm, backbone, S, x, K, num_betas=10, **kw):
+    from oracle import multihmr_ref, smplx_ref
+
+    cfg = multihmr_ref.RefConfig(backbone=backbone, img_size=S, num_betas=num_betas)
+    with torch.no_grad():
+        return multihmr_ref.model_forward(sd, smplx_ref.SMPLXShim(bm, num_betas), cfg, x, K, **kw)
+
+
+def test_num_betas_11_layer(cuda_device):
+    """Model(num_betas=11) uses the 'neutral_11' SMPL-X layer (model.py:104-110, :319): 11 shape components."""
+    from multihmr_b200 import synth
+    from multihmr_b200.model import Model
+
+    backbone, S, B, seed = "dinov2_vits14", 224, 2, 31
+    sd = synth.make_state_dict(backbone, S, num_betas=11, seed=seed)
+    bm = synth.make_body_model(seed)
+    x, K = synth.make_images(B, S, seed), synth.make_cameras(B, S, jitter=True, seed=seed)
+    idx = synth.make_forced_idx(B, S // 14, [2, 1], seed)
+    ref = _oracle_cpu(sd, bm, backbone, S, x, K, num_betas=11, idx=idx, is_training=True)
+    m = Model(backbone=backbone, img_size=S, num_betas=11, max_batch=B, max_persons=8, body_model=bm)
+    m.load_state_dict(sd)
+    out = m(x, idx=idx, K=K, is_training=True)
+    assert out["shape"].shape == (3, 11)
+    bad = pu.compare(out, {k: v.float() for k, v in ref.items()},
+                     ["shape", "rotmat", "expression", "dist", "v3d", "j3d", "transl"], verbose=True)
+    assert not bad, bad
+
+
+def test_nms_off_threshold_list_and_partial_batch(cuda_device):
+    """nms_kernel_size=1 (forward_model's default, demo.py:110), det_thresh given as a list
+    (model.py:614-615), and a batch smaller than max_batch."""
+    from multihmr_b200 import synth
+
+    backbone, S, seed = "dinov2_vits14", 224, 11
+    sd = synth.make_state_dict(backbone, S, seed=seed, det_bias=-1.6)
+    bm = synth.make_body_model(seed)
+    x, K = synth.make_images(2, S, seed), synth.make_cameras(2, S, seed=seed)
+    m = pu.build_engine(dict(backbone=backbone, img_size=S, batch=4), sd, bm, max_batch=4, max_persons=128)
+    persons = m(x, K=K, det_thresh=[0.3], nms_kernel_size=1)
+    ref = _oracle_cpu(sd, bm, backbone, S, x, K, det_thresh=[0.3], nms_kernel_size=1)
+    s_ref = torch.stack([p["scores"] for p in ref])
+    near = ((s_ref - 0.3).abs() < 1e-3).sum().item()
+    assert abs(len(persons) - len(ref)) <= near
+    if len(persons) == len(ref):
+        got = {k: torch.stack([p[k] for p in persons]) for k in ("scores", "loc", "v3d", "transl")}
+        want = {k: torch.stack([p[k] for p in ref]) for k in got}
+        assert not pu.compare(got, want, list(got), verbose=True)
