@@ -17,6 +17,7 @@
 //   * the last key tile only computes the 16-column groups that hold real keys (QK^T with N = 16..128,
 //     PV with K = 16..128, softmax over the needed 32-column chunks);
 //   * softmax warps whose 32 query rows are all beyond T only keep the barrier protocol alive.
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -62,8 +63,8 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   return r;
 }
 
-// kExpMode 0: every exponential on MUFU.EX2; 1: three pairs of eight on the FMA pipes (cubic polynomial,
-// relative error 7.5e-5, far below the fp16 rounding of P).
+// kExpMode = how many of every eight score pairs take their exponential on the FMA pipes (cubic polynomial,
+// relative error 7.5e-5, far below the fp16 rounding of P) instead of MUFU.EX2: 0 (all MUFU) .. 3.
 template <int kExpMode>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
@@ -96,6 +97,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   const int last_valid = T - (n_kv - 1) * kBlockKV;
   const int last_cols = (last_valid + 15) & ~15;
 
+  griddep_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
@@ -118,6 +120,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // qkv of the preceding GEMM is complete and visible
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -207,8 +210,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
 
       // One key tile of the online softmax with NCH (compile-time) 32-column chunks: 4 for full tiles, fewer
       // for the ragged last tile.  Static chunk counts keep the 128 scores in registers (no local memory).
-      auto softmax_tile = [&](auto nch_c, int j) {
+      auto softmax_tile = [&](auto nch_c, auto last_c, int j) {
         constexpr int NCH = decltype(nch_c)::value;
+        constexpr bool kLast = decltype(last_c)::value;  // static: the key mask costs 2 instructions per score
         mbar_wait(s_full, j & 1u);
         tc_fence_after();
         uint32_t s[NCH][32];
@@ -219,14 +223,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);
 
-        if (NCH < 4 || last_valid < kBlockKV) {
-          if (j == n_kv - 1) {  // keys beyond T (or rows of the next image): -inf
+        if constexpr (kLast) {  // keys beyond T (or rows of the next image): -inf
 #pragma unroll
-            for (int c = 0; c < NCH; ++c)
+          for (int c = 0; c < NCH; ++c)
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= last_valid) s[c][i] = 0xff800000u;
-          }
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= last_valid) s[c][i] = 0xff800000u;
         }
         // row max: independent chains (3-input max), then combine
         float mx = -INFINITY;
@@ -257,8 +259,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
             const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
             const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
             const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
-            const bool poly0 = (kExpMode == 1) && (pair == 0 || pair == 4);
-            const bool poly1 = (kExpMode == 1) && (pair + 1 == 3);
+            const bool poly0 = (kExpMode >= 1 && pair == 0) || (kExpMode >= 2 && pair == 4);
+            const bool poly1 = (kExpMode >= 3) && (pair + 1 == 3);
             const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
             const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
             acc0 = __fadd2_rn(acc0, e0);
@@ -294,12 +296,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
       };
 
       const int last_nch = (last_cols + 31) >> 5;  // 32-column chunks of the last tile that hold real keys
-      for (int j = 0; j < n_kv - 1; ++j) softmax_tile(std::integral_constant<int, 4>{}, j);
+      for (int j = 0; j < n_kv - 1; ++j) softmax_tile(std::integral_constant<int, 4>{}, std::false_type{}, j);
       switch (last_nch) {
-        case 1: softmax_tile(std::integral_constant<int, 1>{}, n_kv - 1); break;
-        case 2: softmax_tile(std::integral_constant<int, 2>{}, n_kv - 1); break;
-        case 3: softmax_tile(std::integral_constant<int, 3>{}, n_kv - 1); break;
-        default: softmax_tile(std::integral_constant<int, 4>{}, n_kv - 1); break;
+        case 1: softmax_tile(std::integral_constant<int, 1>{}, std::true_type{}, n_kv - 1); break;
+        case 2: softmax_tile(std::integral_constant<int, 2>{}, std::true_type{}, n_kv - 1); break;
+        case 3: softmax_tile(std::integral_constant<int, 3>{}, std::true_type{}, n_kv - 1); break;
+        default: softmax_tile(std::integral_constant<int, 4>{}, std::true_type{}, n_kv - 1); break;
       }
 
       // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
@@ -339,7 +341,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   }
 }
 
-int g_attn_exp_mode = 0;
+int g_attn_exp_mode = -1;  // -1: not chosen yet (MHMR_ATTN_EXP, else kDefaultExpMode)
+constexpr int kDefaultExpMode = 0;
 
 }  // namespace
 
@@ -360,14 +363,34 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   if (!attr_set) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     attr_set = true;
+  }
+  if (g_attn_exp_mode < 0) {
+    const char* e = std::getenv("MHMR_ATTN_EXP");
+    g_attn_exp_mode = (e != nullptr && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : kDefaultExpMode;
   }
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   dim3 grid((T + kBlockQ - 1) / kBlockQ, D / kHeadDim, B);
-  if (g_attn_exp_mode == 1)
-    attn_fwd_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2);
-  else
-    attn_fwd_kernel<0><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm, out, ldo, T, D, scale_log2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = kAttnSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  auto kern = attn_fwd_kernel<0>;
+  switch (g_attn_exp_mode) {
+    case 1: kern = attn_fwd_kernel<1>; break;
+    case 2: kern = attn_fwd_kernel<2>; break;
+    case 3: kern = attn_fwd_kernel<3>; break;
+    default: break;
+  }
+  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, out, static_cast<int64_t>(ldo), T, D, scale_log2));
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }

@@ -16,6 +16,14 @@
 
 namespace mhmr {
 
+// Programmatic dependent launch (PDL).  Every kernel of the chain lets the next grid start its prologue
+// (barrier init, TMEM allocation, descriptor prefetch) while this grid drains, and waits for the full
+// completion (and memory visibility) of the previous grid before it touches global memory.  Both are no-ops
+// when the kernel was launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+
 // ----------------------------------------------------------------------------------
 // Host-side error plumbing: every C-ABI entry returns an int (0 ok, <0 error) and
 // leaves a message retrievable through mhmr_last_error().
@@ -49,6 +57,8 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, CUtensorMapDataType dtype, 
                  uint32_t box_cols, bool swizzle128);
 
 int device_sm_count();
+// Programmatic dependent launch for the back-to-back kernels of the ViT loop (MHMR_PDL=0 disables).
+bool pdl_enabled();
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------

@@ -59,6 +59,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK - 1) / BK;
 
+  griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -79,6 +80,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // the previous kernel's outputs (A rows, residual, statistics) are complete and visible
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -180,8 +182,17 @@ int launch_one(const GemmPlan* p, cudaStream_t stream) {
                                          Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<p->grid, kThreads, Cfg::kSmemBytes, stream>>>(p->tmA, p->tmB, p->M, p->N, p->K, p->ep);
-  MHMR_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p->tmA, p->tmB, p->M, p->N, p->K, p->ep));
   return MHMR_OK;
 }
 

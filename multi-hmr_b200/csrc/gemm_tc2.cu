@@ -119,6 +119,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK2 - 1) / BK2;
 
+  griddep_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -138,6 +139,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated in both
   tc_fence_after();
+  griddep_wait();  // the previous kernel's outputs (A rows, residual, statistics) are complete and visible
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -246,13 +248,15 @@ int launch_2cta(const GemmPlan* p, cudaStream_t stream) {
   cfg.blockDim = dim3(kThreads2);
   cfg.dynamicSmemBytes = kSmemBytes2;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p->tmA, p->tmB, p->M, p->N, p->K, p->ep));
   return MHMR_OK;
 }

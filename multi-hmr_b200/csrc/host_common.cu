@@ -1,4 +1,5 @@
 // Host-side utilities shared by all translation units of libmhmr_sm100.so.
+#include <cstdlib>
 #include "common.cuh"
 
 #include <mutex>
@@ -74,6 +75,15 @@ int device_sm_count() {
       sms = 148;
   }
   return sms;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = std::getenv("MHMR_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 }  // namespace mhmr

@@ -25,7 +25,7 @@ def _ref(qkv, B, T, D):
     (1, 384 + 100, 64, 1.0),# tail of 100 keys: 112 columns, four chunks
     (1, 33, 64, 1.0),       # one short tile, query warps 2..3 have no rows
 ])
-@pytest.mark.parametrize("exp_mode", [0, 1])
+@pytest.mark.parametrize("exp_mode", [0, 1, 3])
 def test_attention_matches_fp32(cuda_device, B, T, D, scale, exp_mode):
     from multihmr_b200 import ops
 
