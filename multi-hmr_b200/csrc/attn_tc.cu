@@ -17,6 +17,7 @@
 //   * the last key tile only computes the 16-column groups that hold real keys (QK^T with N = 16..128,
 //     PV with K = 16..128, softmax over the needed 32-column chunks);
 //   * softmax warps whose 32 query rows are all beyond T only keep the barrier protocol alive.
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -29,10 +30,13 @@ namespace {
 constexpr int kHeadDim = 64;
 constexpr int kBlockQ = 128;
 constexpr int kBlockKV = 128;
-constexpr int kStagesKV = 2;
 constexpr int kAttnThreads = 192;
 constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: Q, K or V tile
-constexpr int kAttnSmem = kTileBytes * (1 + 2 * kStagesKV) + 1024 + 1024;  // tiles + barriers + align
+constexpr int kBarrierBytes = 256;  // 17 mbarriers + the TMEM slot
+// Q tile + K ring + V ring + 1 KB that covers both the 1024-byte alignment of the tiles and the barriers
+// (in front of the tiles when the alignment pad leaves room, behind them otherwise).  With 3 + 3 stages
+// this is 115712 B: exactly two CTAs per SM ((115712 + 1024 reserved) * 2 = 228 KB).
+constexpr int attn_smem_bytes(int sk, int sv) { return kTileBytes * (1 + sk + sv) + 1024; }
 
 constexpr uint32_t kColS = 0;
 constexpr uint32_t kColP = 128;
@@ -65,7 +69,7 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 
 // kExpMode = how many of every eight score pairs take their exponential on the FMA pipes (cubic polynomial,
 // relative error 7.5e-5, far below the fp16 rounding of P) instead of MUFU.EX2: 0 (all MUFU) .. 3.
-template <int kExpMode>
+template <int kExpMode, int kSK, int kSV, int kAb = 0>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
                 int T, int D, float scale_log2) {
@@ -74,14 +78,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   // shared address space (a round trip through uintptr_t degrades every access to generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + kTileBytes;                     // [kStagesKV]
-  uint8_t* sV = smem + kTileBytes * (1 + kStagesKV);   // [kStagesKV]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTileBytes * (1 + 2 * kStagesKV));
+  uint8_t* sK = smem + kTileBytes;               // [kSK]
+  uint8_t* sV = smem + kTileBytes * (1 + kSK);   // [kSV]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((smem - smem_raw) >= kBarrierBytes ? smem_raw
+                                                                                  : smem + kTileBytes * (1 + kSK + kSV));
   uint64_t* q_full = bars;                 // 1
-  uint64_t* k_full = bars + 1;             // [kStagesKV]
-  uint64_t* v_full = k_full + kStagesKV;   // [kStagesKV]
-  uint64_t* kv_empty = v_full + kStagesKV; // [kStagesKV]
-  uint64_t* s_full = kv_empty + kStagesKV; // MMA -> softmax : S_j complete
+  uint64_t* k_full = bars + 1;             // [kSK]  TMA -> MMA
+  uint64_t* v_full = k_full + kSK;         // [kSV]  TMA -> MMA
+  uint64_t* k_empty = v_full + kSV;        // [kSK]  MMA -> TMA : Q K_j^T complete
+  uint64_t* v_empty = k_empty + kSK;       // [kSV]  MMA -> TMA : P_j V_j complete
+  uint64_t* s_full = v_empty + kSV;        // MMA -> softmax : S_j complete
   uint64_t* s_empty = s_full + 1;          // softmax -> MMA : S_j now in registers
   uint64_t* p_full = s_empty + 1;          // softmax -> MMA : P_j in TMEM (and O rescaled)
   uint64_t* pv_done = p_full + 1;          // MMA -> softmax : O += P_j V_j complete
@@ -102,10 +108,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
       mbar_init(q_full, 1);
-      for (int s = 0; s < kStagesKV; ++s) {
+      for (int s = 0; s < kSK; ++s) {
         mbar_init(&k_full[s], 1);
+        mbar_init(&k_empty[s], 1);
+      }
+      for (int s = 0; s < kSV; ++s) {
         mbar_init(&v_full[s], 1);
-        mbar_init(&kv_empty[s], 1);
+        mbar_init(&v_empty[s], 1);
       }
       mbar_init(s_full, 1);
       mbar_init(s_empty, 4);
@@ -127,14 +136,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, kTileBytes);
       tma_load_2d(sQ, &tmQKV, q_full, head * kHeadDim, row0 + q0);
+      // The K ring is released by Q K^T, the V ring by P V: the loads run up to kSK / kSV key tiles ahead,
+      // which hides the L2 -> smem latency (about one whole tile iteration) behind the softmax.
       for (int j = 0; j < n_kv; ++j) {
-        const int s = j % kStagesKV;
-        const uint32_t ph = (j / kStagesKV) & 1u;
-        mbar_wait(&kv_empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&k_full[s], kTileBytes);
-        tma_load_2d(sK + s * kTileBytes, &tmQKV, &k_full[s], D + head * kHeadDim, row0 + j * kBlockKV);
-        mbar_arrive_expect_tx(&v_full[s], kTileBytes);
-        tma_load_2d(sV + s * kTileBytes, &tmQKV, &v_full[s], 2 * D + head * kHeadDim,
+        const int sk = j % kSK, sv = j % kSV;
+        mbar_wait(&k_empty[sk], ((j / kSK) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&k_full[sk], kTileBytes);
+        tma_load_2d(sK + sk * kTileBytes, &tmQKV, &k_full[sk], D + head * kHeadDim, row0 + j * kBlockKV);
+        mbar_wait(&v_empty[sv], ((j / kSV) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&v_full[sv], kTileBytes);
+        tma_load_2d(sV + sv * kTileBytes, &tmQKV, &v_full[sv], 2 * D + head * kHeadDim,
                     row0 + j * kBlockKV);
       }
     }
@@ -148,15 +159,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
       const uint64_t q_desc = make_sw128_desc(smem_u32(sQ), 16, 1024);
 
       auto issue_qk = [&](int j) {
-        const int s = j % kStagesKV;
+        const int s = j % kSK;
         const int ncols = (j == n_kv - 1) ? last_cols : kBlockKV;
         const uint32_t idesc_qk = make_idesc_f16(128, ncols, false, false);
-        mbar_wait(&k_full[s], (j / kStagesKV) & 1u);
+        mbar_wait(&k_full[s], (j / kSK) & 1u);
         tc_fence_after();
         const uint64_t k_desc = make_sw128_desc(smem_u32(sK + s * kTileBytes), 16, 1024);
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k)
           umma_f16_ss(t_s, q_desc + 2u * k, k_desc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
+        umma_commit(&k_empty[s]);
         umma_commit(s_full);
       };
 
@@ -168,8 +180,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
           tc_fence_after();
           issue_qk(j + 1);
         }
-        const int s = j % kStagesKV;
-        mbar_wait(&v_full[s], (j / kStagesKV) & 1u);
+        const int s = j % kSV;
+        mbar_wait(&v_full[s], (j / kSV) & 1u);
         mbar_wait(p_full, j & 1u);
         tc_fence_after();
         // V tile: 128 keys (K) x 64 dims (N), N contiguous: MN-major, 8-key groups 1024 B apart.
@@ -179,7 +191,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
           // A: 16 fp16 of P = 8 TMEM columns per K step; B: 16 keys = 2048 B per K step
           umma_f16_ts(t_o, t_p + 8u * k, v_desc + 128u * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&kv_empty[s]);
+        umma_commit(&v_empty[s]);
         umma_commit(pv_done);
       }
     }
@@ -232,8 +244,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         }
         // row max: independent chains (3-input max), then combine
         float mx = -INFINITY;
+        if constexpr (kAb == 2 || kAb == 3 || kAb == 4) mx = fmaxf(__uint_as_float(s[0][0]), __uint_as_float(s[0][1]));
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = 0; c < ((kAb == 2 || kAb == 3 || kAb == 4) ? 0 : NCH); ++c) {
           float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
 #pragma unroll
           for (int i = 2; i < 32; i += 2)
@@ -256,13 +269,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         for (int c = 0; c < NCH; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
+            if constexpr (kAb == 4) { p[c][i / 2] = s[c][i]; p[c][i / 2 + 1] = s[c][i + 2]; continue; }
             const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
             const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
             const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
             const bool poly0 = (kExpMode >= 1 && pair == 0) || (kExpMode >= 2 && pair == 4);
             const bool poly1 = (kExpMode >= 3) && (pair + 1 == 3);
-            const float2 e0 = poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
-            const float2 e1 = poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
+            const float2 e0 = (kAb == 1 || kAb == 3 || kAb == 4) ? t0 : poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
+            const float2 e1 = (kAb == 1 || kAb == 3 || kAb == 4) ? t1 : poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
             acc0 = __fadd2_rn(acc0, e0);
             acc1 = __fadd2_rn(acc1, e1);
             const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
@@ -343,6 +357,61 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
 
 int g_attn_exp_mode = -1;  // -1: not chosen yet (MHMR_ATTN_EXP, else kDefaultExpMode)
 constexpr int kDefaultExpMode = 0;
+int g_attn_stages = -1;    // 10 * K stages + V stages (MHMR_ATTN_STAGES, else kDefaultStages)
+constexpr int kDefaultStages = 33;
+int g_attn_ablate = -1;    // MHMR_ATTN_ABLATE: timing experiments only (wrong results), see tools/attn_ablate.py
+
+struct AttnArgs {
+  CUtensorMap tm;
+  __half* out;
+  int64_t ldo;
+  int T, D;
+  float scale_log2;
+  dim3 grid;
+  cudaStream_t stream;
+};
+
+template <int kExpMode, int kSK, int kSV, int kAb>
+int attn_launch(const AttnArgs& a) {
+  constexpr int smem = attn_smem_bytes(kSK, kSV);
+  auto kern = attn_fwd_kernel<kExpMode, kSK, kSV, kAb>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (std::getenv("MHMR_ATTN_VERBOSE") != nullptr) {
+      int ctas = 0;
+      cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, kAttnThreads, smem);
+      fprintf(stderr, "[mhmr] attention<%d,%d,%d,%d>: %d B dynamic smem, occupancy query -> %d CTAs/SM (%s)\n", kExpMode,
+              kSK, kSV, kAb, smem, ctas, cudaGetErrorString(oe));
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = a.grid;
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.tm, a.out, a.ldo, a.T, a.D, a.scale_log2));
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+template <int kSK, int kSV>
+int attn_dispatch(const AttnArgs& a, int exp_mode, int ablate) {
+  if (ablate == 1) return attn_launch<0, kSK, kSV, 1>(a);
+  if (ablate == 4) return attn_launch<0, kSK, kSV, 4>(a);
+  switch (exp_mode) {
+    case 1: return attn_launch<1, kSK, kSV, 0>(a);
+    case 2: return attn_launch<2, kSK, kSV, 0>(a);
+    case 3: return attn_launch<3, kSK, kSV, 0>(a);
+    default: return attn_launch<0, kSK, kSV, 0>(a);
+  }
+}
 
 }  // namespace
 
@@ -355,43 +424,34 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   MHMR_REQUIRE(D % kHeadDim == 0, "attention: embed dim must be a multiple of 64");
   MHMR_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0, "attention: row pitches must be multiples of 8");
   MHMR_REQUIRE(B > 0 && T > 0, "attention: empty problem");
-  CUtensorMap tm;
-  int rc = make_tmap_2d(&tm, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<uint64_t>(B) * T,
+  AttnArgs a;
+  int rc = make_tmap_2d(&a.tm, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<uint64_t>(B) * T,
                         3ull * D, ld_qkv * 2, 128, 64, true);
   if (rc != MHMR_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    attr_set = true;
-  }
   if (g_attn_exp_mode < 0) {
     const char* e = std::getenv("MHMR_ATTN_EXP");
     g_attn_exp_mode = (e != nullptr && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : kDefaultExpMode;
   }
-  const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-  dim3 grid((T + kBlockQ - 1) / kBlockQ, D / kHeadDim, B);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(kAttnThreads);
-  cfg.dynamicSmemBytes = kAttnSmem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  auto kern = attn_fwd_kernel<0>;
-  switch (g_attn_exp_mode) {
-    case 1: kern = attn_fwd_kernel<1>; break;
-    case 2: kern = attn_fwd_kernel<2>; break;
-    case 3: kern = attn_fwd_kernel<3>; break;
-    default: break;
+  if (g_attn_stages < 0) {
+    const char* e = std::getenv("MHMR_ATTN_STAGES");
+    g_attn_stages = (e != nullptr) ? atoi(e) : kDefaultStages;
+    const char* ab = std::getenv("MHMR_ATTN_ABLATE");
+    g_attn_ablate = (ab != nullptr) ? atoi(ab) : 0;
   }
-  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm, out, static_cast<int64_t>(ldo), T, D, scale_log2));
-  MHMR_CUDA_CHECK(cudaGetLastError());
+  a.out = out;
+  a.ldo = ldo;
+  a.T = T;
+  a.D = D;
+  a.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+  a.grid = dim3((T + kBlockQ - 1) / kBlockQ, D / kHeadDim, B);
+  a.stream = stream;
+  switch (g_attn_stages) {
+    case 22: return attn_dispatch<2, 2>(a, g_attn_exp_mode, g_attn_ablate);
+    case 32: return attn_dispatch<3, 2>(a, g_attn_exp_mode, g_attn_ablate);
+    case 23: return attn_dispatch<2, 3>(a, g_attn_exp_mode, g_attn_ablate);
+    case 33: return attn_dispatch<3, 3>(a, g_attn_exp_mode, g_attn_ablate);
+    default: MHMR_REQUIRE(false, "MHMR_ATTN_STAGES must be 22, 32, 23 or 33");
+  }
   return MHMR_OK;
 }
 

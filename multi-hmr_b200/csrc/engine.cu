@@ -48,7 +48,7 @@ struct mhmr_engine {
   mhmr_config cfg{};
   int D = 0, depth = 0, heads = 0, res = 0, N = 0, T = 0, C = 0, Cp = 0, Cq = 0, nkv = 0, ndec = 0;
   bool finalized = false;
-  bool fuse_ln = true;   // LayerNorm folded into the neighbouring GEMM epilogues (MHMR_FUSE_LN=0 disables)
+  bool fuse_ln = false;  // LayerNorm folded into the neighbouring GEMM epilogues (MHMR_FUSE_LN=1 enables; measured slower and less accurate at full size than the separate LN kernel)
   __half* X16 = nullptr;            // fp16 copy of the residual stream (A operand of qkv / fc1 when fused)
   float *statsA = nullptr, *statsB = nullptr;  // [max_batch*T, stat_slots, 2] partial row (sum, sum of squares)
   int stat_slots = 0;
