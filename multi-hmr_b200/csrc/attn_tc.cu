@@ -19,6 +19,7 @@
 //   * softmax warps whose 32 query rows are all beyond T only keep the barrier protocol alive.
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -65,6 +66,15 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(xf.x) << 23));
   r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(xf.y) << 23));
   return r;
+}
+
+// Timeline tracing (MHMR_ATTN_TRACE=file, kAb 7 / 8): SM-clock stamps of the protocol events of a few CTAs.
+__device__ uint32_t* g_attn_trace = nullptr;
+constexpr int kTraceIters = 40, kTraceEvents = 12, kTraceCtas = 8;
+__device__ __forceinline__ uint32_t clk_after(float dep) {
+  uint32_t t;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(t) : "f"(dep) : "memory");
+  return t;
 }
 
 // kExpMode = how many of every eight score pairs take their exponential on the FMA pipes (cubic polynomial,
@@ -130,63 +140,93 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();  // qkv of the preceding GEMM is complete and visible
+  constexpr bool kTrace = (kAb == 7 || kAb == 8);
+  uint32_t* trace = nullptr;
+  if constexpr (kTrace) {
+    const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    // CTAs of the third wave onwards (steady state), every 37th
+    if (g_attn_trace != nullptr && lin >= 600 && (lin - 600) % 37 == 0 && (lin - 600) / 37 < kTraceCtas)
+      trace = g_attn_trace + ((lin - 600) / 37) * kTraceIters * kTraceEvents;
+    if (trace != nullptr && threadIdx.x == 64) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      trace[10] = smid;
+      trace[11] = clk_after(0.f);
+    }
+  }
+  auto stamp = [&](int j, int ev, float dep) {
+    if constexpr (kTrace) {
+      if (trace != nullptr && j < kTraceIters) trace[j * kTraceEvents + ev] = clk_after(dep);
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // (whole warp on uniform control flow; one elected lane issues -- see elect_one_sync)
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, kTileBytes);
       tma_load_2d(sQ, &tmQKV, q_full, head * kHeadDim, row0 + q0);
-      // The K ring is released by Q K^T, the V ring by P V: the loads run up to kSK / kSV key tiles ahead,
-      // which hides the L2 -> smem latency (about one whole tile iteration) behind the softmax.
-      for (int j = 0; j < n_kv; ++j) {
-        const int sk = j % kSK, sv = j % kSV;
-        mbar_wait(&k_empty[sk], ((j / kSK) & 1u) ^ 1u);
+    }
+    // The K ring is released by Q K^T, the V ring by P V: the loads run up to kSK / kSV key tiles ahead,
+    // which hides the L2 -> smem latency (about one whole tile iteration) behind the softmax.
+    for (int j = 0; j < n_kv; ++j) {
+      const int sk = j % kSK, sv = j % kSV;
+      mbar_wait(&k_empty[sk], ((j / kSK) & 1u) ^ 1u);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&k_full[sk], kTileBytes);
         tma_load_2d(sK + sk * kTileBytes, &tmQKV, &k_full[sk], D + head * kHeadDim, row0 + j * kBlockKV);
-        mbar_wait(&v_empty[sv], ((j / kSV) & 1u) ^ 1u);
+      }
+      mbar_wait(&v_empty[sv], ((j / kSV) & 1u) ^ 1u);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&v_full[sv], kTileBytes);
-        tma_load_2d(sV + sv * kTileBytes, &tmQKV, &v_full[sv], 2 * D + head * kHeadDim,
-                    row0 + j * kBlockKV);
+        tma_load_2d(sV + sv * kTileBytes, &tmQKV, &v_full[sv], 2 * D + head * kHeadDim, row0 + j * kBlockKV);
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, false, true);  // B (V) is MN-major
-      const uint32_t t_s = tmem_base + kColS;
-      const uint32_t t_p = tmem_base + kColP;
-      const uint32_t t_o = tmem_base + kColO;
-      const uint64_t q_desc = make_sw128_desc(smem_u32(sQ), 16, 1024);
+    // (whole warp on uniform control flow; one elected lane issues)
+    constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, false, true);  // B (V) is MN-major
+    const uint32_t t_s = tmem_base + kColS;
+    const uint32_t t_p = tmem_base + kColP;
+    const uint32_t t_o = tmem_base + kColO;
+    const uint64_t q_desc = make_sw128_desc(smem_u32(sQ), 16, 1024);
 
-      auto issue_qk = [&](int j) {
-        const int s = j % kSK;
-        const int ncols = (j == n_kv - 1) ? last_cols : kBlockKV;
-        const uint32_t idesc_qk = make_idesc_f16(128, ncols, false, false);
-        mbar_wait(&k_full[s], (j / kSK) & 1u);
-        tc_fence_after();
-        const uint64_t k_desc = make_sw128_desc(smem_u32(sK + s * kTileBytes), 16, 1024);
+    auto issue_qk = [&](int j) {
+      const int s = j % kSK;
+      const int ncols = (j == n_kv - 1) ? last_cols : kBlockKV;
+      const uint32_t idesc_qk = make_idesc_f16(128, ncols, false, false);
+      mbar_wait(&k_full[s], (j / kSK) & 1u);
+      tc_fence_after();
+      const uint64_t k_desc = make_sw128_desc(smem_u32(sK + s * kTileBytes), 16, 1024);
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k)
           umma_f16_ss(t_s, q_desc + 2u * k, k_desc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
         umma_commit(&k_empty[s]);
         umma_commit(s_full);
-      };
+      }
+      __syncwarp();
+    };
 
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
-          mbar_wait(s_empty, j & 1u);  // softmax holds S_j in registers: S may be overwritten
-          tc_fence_after();
-          issue_qk(j + 1);
-        }
-        const int s = j % kSV;
-        mbar_wait(&v_full[s], (j / kSV) & 1u);
-        mbar_wait(p_full, j & 1u);
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) {
+        mbar_wait(s_empty, j & 1u);  // softmax holds S_j in registers: S may be overwritten
         tc_fence_after();
-        // V tile: 128 keys (K) x 64 dims (N), N contiguous: MN-major, 8-key groups 1024 B apart.
-        const uint64_t v_desc = make_sw128_desc(smem_u32(sV + s * kTileBytes), 1024, 1024);
-        const int ksteps = ((j == n_kv - 1) ? last_cols : kBlockKV) / 16;
+        if constexpr (kTrace) { if (lane == 0) stamp(j, 6, 0.f); }
+        issue_qk(j + 1);
+        if constexpr (kTrace) { if (lane == 0) stamp(j, 7, 0.f); }
+      }
+      const int s = j % kSV;
+      mbar_wait(&v_full[s], (j / kSV) & 1u);
+      mbar_wait(p_full, j & 1u);
+      tc_fence_after();
+      if constexpr (kTrace) { if (lane == 0) stamp(j, 8, 0.f); }
+      // V tile: 128 keys (K) x 64 dims (N), N contiguous: MN-major, 8-key groups 1024 B apart.
+      const uint64_t v_desc = make_sw128_desc(smem_u32(sV + s * kTileBytes), 1024, 1024);
+      const int ksteps = ((j == n_kv - 1) ? last_cols : kBlockKV) / 16;
+      if (elect_one_sync()) {
         for (int k = 0; k < ksteps; ++k) {
           // A: 16 fp16 of P = 8 TMEM columns per K step; B: 16 keys = 2048 B per K step
           umma_f16_ts(t_o, t_p + 8u * k, v_desc + 128u * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
@@ -194,6 +234,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         umma_commit(&v_empty[s]);
         umma_commit(pv_done);
       }
+      __syncwarp();
+      if constexpr (kTrace) { if (lane == 0) stamp(j, 9, 0.f); }
     }
   } else {
     // ------------------------------ Softmax warps ------------------------------
@@ -227,10 +269,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         constexpr bool kLast = decltype(last_c)::value;  // static: the key mask costs 2 instructions per score
         mbar_wait(s_full, j & 1u);
         tc_fence_after();
+        if (warp == 2 && lane == 0) stamp(j, 0, 0.f);
         uint32_t s[NCH][32];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
         tmem_ld_wait();
+        if (warp == 2 && lane == 0) stamp(j, 1, __uint_as_float(s[0][0]));
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);
@@ -244,15 +288,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         }
         // row max: independent chains (3-input max), then combine
         float mx = -INFINITY;
-        if constexpr (kAb == 2 || kAb == 3 || kAb == 4) mx = fmaxf(__uint_as_float(s[0][0]), __uint_as_float(s[0][1]));
+        if constexpr (kAb == 2 || kAb == 3 || kAb == 4 || kAb == 8) mx = fmaxf(__uint_as_float(s[0][0]), __uint_as_float(s[0][1]));
 #pragma unroll
-        for (int c = 0; c < ((kAb == 2 || kAb == 3 || kAb == 4) ? 0 : NCH); ++c) {
+        for (int c = 0; c < ((kAb == 2 || kAb == 3 || kAb == 4 || kAb == 8) ? 0 : NCH); ++c) {
           float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
 #pragma unroll
           for (int i = 2; i < 32; i += 2)
             m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
           mx = fmaxf(mx, m0);
         }
+        if (warp == 2 && lane == 0) stamp(j, 2, mx);
         const float m_new = fmaxf(m_used, mx * scale_log2);
         const bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile
         float alpha = 1.0f;
@@ -269,7 +314,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         for (int c = 0; c < NCH; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            if constexpr (kAb == 4) { p[c][i / 2] = s[c][i]; p[c][i / 2 + 1] = s[c][i + 2]; continue; }
+            if constexpr (kAb == 4 || kAb == 8) { p[c][i / 2] = s[c][i]; p[c][i / 2 + 1] = s[c][i + 2]; continue; }
             const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
             const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
             const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
@@ -285,10 +330,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
           }
         }
         l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
+        if (warp == 2 && lane == 0) stamp(j, 3, l);
 
         if (j > 0) {
           mbar_wait(pv_done, (j - 1) & 1u);  // P buffer free, O stable
           tc_fence_after();
+          if (warp == 2 && lane == 0) stamp(j, 4, 0.f);
           if (__any_sync(0xffffffffu, rescale)) {  // rare after the first tiles: small chunks
 #pragma unroll 1
             for (int c = 0; c < kHeadDim / 8; ++c) {
@@ -307,6 +354,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+        if (warp == 2 && lane == 0) stamp(j, 5, 0.f);
       };
 
       const int last_nch = (last_cols + 31) >> 5;  // 32-column chunks of the last tile that hold real keys
@@ -355,6 +403,338 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   }
 }
 
+
+
+// ---------------------------------------------------------------------------------------------------
+// 64-key tiles with double-buffered S and P in TMEM and register-prefetched scores.
+//
+// tcgen05.ld moves 64 B/clk per SM: reading a 128 x 128 fp32 score tile out of TMEM costs as many cycles
+// (1024) as its exponentials on the MUFU pipe, so both have to overlap INSIDE each softmax warp.  With
+// 64-key tiles two S buffers and two P buffers fit in the CTA's 256 TMEM columns next to O:
+//
+//   TMEM  = S0 (64 fp32 cols) | S1 (64) | P0 (32 cols = 64 fp16) | P1 (32) | O (64)
+//   the MMA warp keeps Q K^T two tiles ahead of the softmax: S(j+1) is complete in TMEM while the softmax
+//   warps work on S(j), so they issue the (asynchronous) tcgen05.ld of S(j+1) first, run max / exp2 /
+//   row sum / fp16 packing on the registers of S(j) while the load streams in, store P(j) and go on.
+//
+//   grid  = (ceil(T/128) query tiles, heads, images), 2 CTAs co-resident per SM
+//   CTA   = 192 threads: warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 softmax (1 thread = 1 row)
+//   smem  = Q (16 KB) | K ring (8 KB tiles, released by Q K^T) | V ring (8 KB tiles, released by P V)
+constexpr int kKV3 = 64;
+constexpr int kAttn3Threads = 256;                // 2 warpgroups: {TMA, MMA, 2 idle} | 4 softmax warps
+constexpr int kRegs3Issue = 48, kRegs3Softmax = 208;  // 128 * (48 + 208) = half of the register file per CTA
+constexpr int kTile3Bytes = kKV3 * kHeadDim * 2;  // 8 KB
+constexpr uint32_t kCol3S = 0, kCol3P = 128, kCol3O = 192;
+constexpr int attn3_smem_bytes(int sk, int sv) { return kTileBytes + kTile3Bytes * (sk + sv) + 1024; }
+
+template <int kExpMode, int kSK, int kSV, int kAb = 0>
+__global__ void __launch_bounds__(kAttn3Threads, 2)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 __half* __restrict__ out, int64_t ldo, int T, int D, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kTileBytes;                       // [kSK]
+  uint8_t* sV = smem + kTileBytes + kTile3Bytes * kSK;   // [kSV]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((smem - smem_raw) >= kBarrierBytes
+                                                   ? smem_raw
+                                                   : smem + kTileBytes + kTile3Bytes * (kSK + kSV));
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // [kSK]  TMA -> MMA
+  uint64_t* v_full = k_full + kSK;         // [kSV]  TMA -> MMA
+  uint64_t* k_empty = v_full + kSV;        // [kSK]  MMA -> TMA : Q K_j^T complete
+  uint64_t* v_empty = k_empty + kSK;       // [kSV]  MMA -> TMA : P_j V_j complete
+  uint64_t* s_full = v_empty + kSV;        // [2]    MMA -> softmax : S_j complete in buffer j & 1
+  uint64_t* s_empty = s_full + 2;          // [2]    softmax -> MMA : S_j now in registers
+  uint64_t* p_full = s_empty + 2;          // [2]    softmax -> MMA : P_j in buffer j & 1 (and O rescaled)
+  uint64_t* pv_done = p_full + 2;          // [2]    MMA -> softmax : O += P_j V_j complete (j & 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  static_assert((1 + 2 * kSK + 2 * kSV + 8) * 8 + 4 <= kBarrierBytes, "barrier area too small");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+  const int row0 = img * T;              // first token row of this image in the [B*T, 3D] matrix
+  const int q0 = q_tile * kBlockQ;
+  const int n_kv = (T + kKV3 - 1) / kKV3;
+  // real keys of the last tile, rounded up to the 16-column granularity of the MMAs
+  const int last_valid = T - (n_kv - 1) * kKV3;
+  const int last_cols = (last_valid + 15) & ~15;
+
+  griddep_launch_dependents();
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      mbar_init(q_full, 1);
+      for (int s = 0; s < kSK; ++s) {
+        mbar_init(&k_full[s], 1);
+        mbar_init(&k_empty[s], 1);
+      }
+      for (int s = 0; s < kSV; ++s) {
+        mbar_init(&v_full[s], 1);
+        mbar_init(&v_empty[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&s_full[b], 1);
+        mbar_init(&s_empty[b], 4);
+        mbar_init(&p_full[b], 4);
+        mbar_init(&pv_done[b], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<kTmemCols>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // qkv of the preceding GEMM is complete and visible
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs3Issue));
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_2d(sQ, &tmQ, q_full, head * kHeadDim, row0 + q0);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int sk = j % kSK, sv = j % kSV;
+      mbar_wait(&k_empty[sk], ((j / kSK) & 1u) ^ 1u);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&k_full[sk], kTile3Bytes);
+        tma_load_2d(sK + sk * kTile3Bytes, &tmKV, &k_full[sk], D + head * kHeadDim, row0 + j * kKV3);
+      }
+      mbar_wait(&v_empty[sv], ((j / kSV) & 1u) ^ 1u);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&v_full[sv], kTile3Bytes);
+        tma_load_2d(sV + sv * kTile3Bytes, &tmKV, &v_full[sv], 2 * D + head * kHeadDim, row0 + j * kKV3);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs3Issue));
+    constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, false, true);  // B (V) is MN-major
+    const uint64_t q_desc = make_sw128_desc(smem_u32(sQ), 16, 1024);
+    const uint32_t t_o = tmem_base + kCol3O;
+
+    auto issue_qk = [&](int j) {  // S_j -> buffer j & 1
+      const int s = j % kSK;
+      const int ncols = (j == n_kv - 1) ? last_cols : kKV3;
+      const uint32_t idesc_qk = make_idesc_f16(128, ncols, false, false);
+      mbar_wait(&k_full[s], (j / kSK) & 1u);
+      tc_fence_after();
+      const uint64_t k_desc = make_sw128_desc(smem_u32(sK + s * kTile3Bytes), 16, 1024);
+      const uint32_t t_s = tmem_base + kCol3S + (j & 1) * kKV3;
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_f16_ss(t_s, q_desc + 2u * k, k_desc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
+        umma_commit(&k_empty[s]);
+        umma_commit(&s_full[j & 1]);
+      }
+      __syncwarp();
+    };
+
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    if (n_kv > 1) issue_qk(1);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j >= 1 && j + 1 < n_kv) {
+        // buffer (j+1) & 1 held S_{j-1}: free once the softmax warps have it in registers
+        mbar_wait(&s_empty[(j + 1) & 1], ((j - 1) >> 1) & 1u);
+        tc_fence_after();
+        issue_qk(j + 1);
+      }
+      const int s = j % kSV;
+      mbar_wait(&v_full[s], (j / kSV) & 1u);
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1u);
+      tc_fence_after();
+      // V tile: 64 keys (K) x 64 dims (N), N contiguous: MN-major, 8-key groups 1024 B apart.
+      const uint64_t v_desc = make_sw128_desc(smem_u32(sV + s * kTile3Bytes), 1024, 1024);
+      const uint32_t t_p = tmem_base + kCol3P + (j & 1) * (kKV3 / 2);
+      const int ksteps = ((j == n_kv - 1) ? last_cols : kKV3) / 16;
+      if (elect_one_sync()) {
+        for (int k = 0; k < ksteps; ++k) {
+          // A: 16 fp16 of P = 8 TMEM columns per K step; B: 16 keys = 2048 B per K step
+          umma_f16_ts(t_o, t_p + 8u * k, v_desc + 128u * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[s]);
+        umma_commit(&pv_done[j & 1]);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs3Issue));
+  } else {
+    // ------------------------------ Softmax warps ------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs3Softmax));
+    const int sub = warp & 3;             // TMEM sub-partition (lane quarter) of this warp
+    const int row = sub * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(sub * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + kCol3S;
+    const uint32_t t_p = tmem_base + lane_base + kCol3P;
+    const uint32_t t_o = tmem_base + lane_base + kCol3O;
+    const bool warp_has_rows = (q0 + sub * 32) < T;  // warp-uniform
+
+    if (!warp_has_rows) {
+      // All 32 rows of this warp are beyond the sequence: their S/P/O lanes hold garbage that is never
+      // stored and never mixes with other rows (the MMAs are row-independent); keep the protocol alive.
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&s_full[j & 1], (j >> 1) & 1u);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_empty[j & 1]);
+          mbar_arrive(&p_full[j & 1]);
+        }
+      }
+    } else {
+      float m_used = -INFINITY;  // running max (log2 domain) actually used as the exponent offset
+      float l = 0.0f;
+      uint32_t sA[2][32], sB[2][32];
+
+      // One 64-key tile of the online softmax.  `cur` holds S_j; the load of S_{j+1} into `nxt` is issued
+      // first and only waited for at the end, so it streams out of TMEM underneath the exponentials.
+      auto process = [&](uint32_t (&cur)[2][32], uint32_t (&nxt)[2][32], int j) {
+        const int b = j & 1;
+        const bool more = (j + 1 < n_kv);
+        if (more) {
+          mbar_wait(&s_full[b ^ 1], ((j + 1) >> 1) & 1u);
+          tc_fence_after();
+          tmem_ld_32x32(t_s + (b ^ 1) * kKV3, nxt[0]);
+          tmem_ld_32x32(t_s + (b ^ 1) * kKV3 + 32, nxt[1]);
+        }
+        if (j == n_kv - 1) {  // keys beyond T (or rows of the next image): -inf
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (c * 32 + k >= last_valid) cur[c][k] = 0xff800000u;
+        }
+        // row max: independent chains (3-input max), then combine
+        float mx = -INFINITY;
+        if constexpr (kAb == 4) mx = fmaxf(__uint_as_float(cur[0][0]), __uint_as_float(cur[0][1]));
+#pragma unroll
+        for (int c = 0; c < (kAb == 4 ? 0 : 2); ++c) {
+          float m0 = fmaxf(__uint_as_float(cur[c][0]), __uint_as_float(cur[c][1]));
+#pragma unroll
+          for (int k = 2; k < 32; k += 2)
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[c][k]), __uint_as_float(cur[c][k + 1])));
+          mx = fmaxf(mx, m0);
+        }
+        const float m_new = fmaxf(m_used, mx * scale_log2);
+        const bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile
+        float alpha = 1.0f;
+        if (rescale) {
+          alpha = exp2f(m_used - m_new);  // 0 on the first tile
+          m_used = m_new;
+        }
+        // exponentials (MUFU.EX2), packed f32x2 FMA/ADD, two accumulator pairs
+        const float2 sc2 = make_float2(scale_log2, scale_log2);
+        const float2 nm2 = make_float2(-m_used, -m_used);
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        uint32_t p[2][16];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            if constexpr (kAb == 4) { p[c][k / 2] = cur[c][k]; p[c][k / 2 + 1] = cur[c][k + 2]; continue; }
+            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(cur[c][k]), __uint_as_float(cur[c][k + 1])), sc2, nm2);
+            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(cur[c][k + 2]), __uint_as_float(cur[c][k + 3])), sc2, nm2);
+            const int pair = (k >> 1) & 7;  // pair index within a group of 8 pairs
+            const bool poly0 = (kExpMode >= 1 && pair == 0) || (kExpMode >= 2 && pair == 4);
+            const bool poly1 = (kExpMode >= 3) && (pair + 1 == 3);
+            const float2 e0 = (kAb == 1) ? t0 : poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
+            const float2 e1 = (kAb == 1) ? t1 : poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
+            acc0 = __fadd2_rn(acc0, e0);
+            acc1 = __fadd2_rn(acc1, e1);
+            const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
+            p[c][k / 2] = *reinterpret_cast<const uint32_t*>(&h0);
+            p[c][k / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+          }
+        }
+        l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
+
+        if (j >= 2) mbar_wait(&pv_done[b], ((j >> 1) - 1) & 1u);  // P V_{j-2} complete: P buffer b is free
+        if (j >= 1 && __any_sync(0xffffffffu, rescale)) {           // rare after the first tiles
+          mbar_wait(&pv_done[b ^ 1], ((j - 1) >> 1) & 1u);          // P V_{j-1} complete: O is stable
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < kHeadDim / 8; ++c) {
+            uint32_t o[8];
+            tmem_ld_32x8(t_o + c * 8, o);
+            tmem_ld_wait();  // (also completes the S prefetch: harmless, this path is rare)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            tmem_st_32x8(t_o + c * 8, o);
+          }
+        }
+        tc_fence_after();
+        tmem_st_32x16(t_p + b * (kKV3 / 2), p[0]);
+        tmem_st_32x16(t_p + b * (kKV3 / 2) + 16, p[1]);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[b]);
+        if (more) {
+          tmem_ld_wait();  // S_{j+1} is in registers: its TMEM buffer may be overwritten by Q K_{j+3}^T
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[b ^ 1]);
+        }
+      };
+
+      mbar_wait(&s_full[0], 0);
+      tc_fence_after();
+      tmem_ld_32x32(t_s, sA[0]);
+      tmem_ld_32x32(t_s + 32, sA[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[0]);
+      for (int j = 0; j < n_kv; j += 2) {
+        process(sA, sB, j);
+        if (j + 1 < n_kv) process(sB, sA, j + 1);
+      }
+
+      // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
+      mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1u);
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      const int q = q0 + row;
+      __half* dst = out + static_cast<int64_t>(row0 + q) * ldo + head * kHeadDim;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32(t_o + c * 32, o);
+        tmem_ld_wait();
+        if (q < T) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const __half2 h = __floats2half2_rn(__uint_as_float(o[g * 8 + 2 * k]) * inv_l,
+                                                  __uint_as_float(o[g * 8 + 2 * k + 1]) * inv_l);
+              pw[k] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
 int g_attn_exp_mode = -1;  // -1: not chosen yet (MHMR_ATTN_EXP, else kDefaultExpMode)
 constexpr int kDefaultExpMode = 0;
 int g_attn_stages = -1;    // 10 * K stages + V stages (MHMR_ATTN_STAGES, else kDefaultStages)
@@ -362,7 +742,8 @@ constexpr int kDefaultStages = 33;
 int g_attn_ablate = -1;    // MHMR_ATTN_ABLATE: timing experiments only (wrong results), see tools/attn_ablate.py
 
 struct AttnArgs {
-  CUtensorMap tm;
+  CUtensorMap tm;     // 128-row boxes (Q; K and V of the 128-key kernel)
+  CUtensorMap tm_kv;  // 64-row boxes (K and V of the 64-key kernel)
   __half* out;
   int64_t ldo;
   int T, D;
@@ -401,8 +782,46 @@ int attn_launch(const AttnArgs& a) {
   return MHMR_OK;
 }
 
+template <int kExpMode, int kSK, int kSV, int kAb>
+int attn3_launch(const AttnArgs& a) {
+  constexpr int smem = attn3_smem_bytes(kSK, kSV);
+  auto kern = attn_fwd3_kernel<kExpMode, kSK, kSV, kAb>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = a.grid;
+  cfg.blockDim = dim3(kAttn3Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.tm, a.tm_kv, a.out, a.ldo, a.T, a.D, a.scale_log2));
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+template <int kSK, int kSV>
+int attn3_dispatch(const AttnArgs& a, int exp_mode, int ablate) {
+  if (ablate == 1) return attn3_launch<0, kSK, kSV, 1>(a);
+  if (ablate == 4) return attn3_launch<0, kSK, kSV, 4>(a);
+  switch (exp_mode) {
+    case 1: return attn3_launch<1, kSK, kSV, 0>(a);
+    case 2: return attn3_launch<2, kSK, kSV, 0>(a);
+    case 3: return attn3_launch<3, kSK, kSV, 0>(a);
+    default: return attn3_launch<0, kSK, kSV, 0>(a);
+  }
+}
+
 template <int kSK, int kSV>
 int attn_dispatch(const AttnArgs& a, int exp_mode, int ablate) {
+  if (ablate == 7) return attn_launch<0, kSK, kSV, 7>(a);
+  if (ablate == 8) return attn_launch<0, kSK, kSV, 8>(a);
   if (ablate == 1) return attn_launch<0, kSK, kSV, 1>(a);
   if (ablate == 4) return attn_launch<0, kSK, kSV, 4>(a);
   switch (exp_mode) {
@@ -428,6 +847,9 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   int rc = make_tmap_2d(&a.tm, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<uint64_t>(B) * T,
                         3ull * D, ld_qkv * 2, 128, 64, true);
   if (rc != MHMR_OK) return rc;
+  rc = make_tmap_2d(&a.tm_kv, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<uint64_t>(B) * T, 3ull * D,
+                    ld_qkv * 2, kKV3, 64, true);
+  if (rc != MHMR_OK) return rc;
   if (g_attn_exp_mode < 0) {
     const char* e = std::getenv("MHMR_ATTN_EXP");
     g_attn_exp_mode = (e != nullptr && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : kDefaultExpMode;
@@ -445,7 +867,30 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   a.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   a.grid = dim3((T + kBlockQ - 1) / kBlockQ, D / kHeadDim, B);
   a.stream = stream;
+  const char* trace_path = std::getenv("MHMR_ATTN_TRACE");
+  uint32_t* d_trace = nullptr;
+  const size_t trace_words = static_cast<size_t>(kTraceCtas) * kTraceIters * kTraceEvents;
+  if (trace_path != nullptr && (g_attn_ablate == 7 || g_attn_ablate == 8)) {
+    MHMR_CUDA_CHECK(cudaMalloc(&d_trace, trace_words * 4));
+    MHMR_CUDA_CHECK(cudaMemset(d_trace, 0, trace_words * 4));
+    MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &d_trace, sizeof(d_trace)));
+    rc = attn_dispatch<3, 3>(a, g_attn_exp_mode, g_attn_ablate);
+    if (rc != MHMR_OK) return rc;
+    MHMR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    std::vector<uint32_t> h(trace_words);
+    MHMR_CUDA_CHECK(cudaMemcpy(h.data(), d_trace, trace_words * 4, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "wb")) {
+      fwrite(h.data(), 4, trace_words, f);
+      fclose(f);
+    }
+    cudaFree(d_trace);
+    d_trace = nullptr;
+    MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &d_trace, sizeof(d_trace)));
+    return MHMR_OK;
+  }
   switch (g_attn_stages) {
+    case 344: return attn3_dispatch<4, 4>(a, g_attn_exp_mode, g_attn_ablate);
+    case 355: return attn3_dispatch<5, 5>(a, g_attn_exp_mode, g_attn_ablate);
     case 22: return attn_dispatch<2, 2>(a, g_attn_exp_mode, g_attn_ablate);
     case 32: return attn_dispatch<3, 2>(a, g_attn_exp_mode, g_attn_ablate);
     case 23: return attn_dispatch<2, 3>(a, g_attn_exp_mode, g_attn_ablate);

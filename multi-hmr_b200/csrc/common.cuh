@@ -68,6 +68,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+// One leader lane of a fully active warp (the same lane every time).  Issue loops (TMA, tcgen05.mma) run
+// with the WHOLE warp on warp-uniform control flow and guard only the issuing instructions with this
+// predicate: their descriptors then live in uniform registers.  Under `if (lane == 0)` the compiler cannot
+// prove uniformity and wraps every TMA / MMA / commit in an elect-and-retry loop (~80 clk per instruction).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 
 // ---- mbarrier -------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
