@@ -33,7 +33,7 @@ constexpr int kBlockQ = 128;
 constexpr int kBlockKV = 128;
 constexpr int kAttnThreads = 192;
 constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: Q, K or V tile
-constexpr int kBarrierBytes = 256;  // 17 mbarriers + the TMEM slot
+constexpr int kBarrierBytes = 512;  // mbarriers + the TMEM slot
 // Q tile + K ring + V ring + 1 KB that covers both the 1024-byte alignment of the tiles and the barriers
 // (in front of the tiles when the alignment pad leaves room, behind them otherwise).  With 3 + 3 stages
 // this is 115712 B: exactly two CTAs per SM ((115712 + 1024 reserved) * 2 = 228 KB).
@@ -70,11 +70,19 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 
 // Timeline tracing (MHMR_ATTN_TRACE=file, kAb 7 / 8): SM-clock stamps of the protocol events of a few CTAs.
 __device__ uint32_t* g_attn_trace = nullptr;
-constexpr int kTraceIters = 40, kTraceEvents = 12, kTraceCtas = 8;
+constexpr int kTraceIters = 40, kTraceEvents = 16, kTraceCtas = 8;
 __device__ __forceinline__ uint32_t clk_after(float dep) {
   uint32_t t;
   asm volatile("mov.u32 %0, %%clock;" : "=r"(t) : "f"(dep) : "memory");
   return t;
+}
+
+// A condition the compilers cannot fold (always true).  ptxas schedules within basic blocks: a branch on it
+// keeps the instructions that follow from being woven into the instructions before it.
+__device__ __forceinline__ bool opaque_true() {
+  uint32_t v;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(v)::"memory");
+  return v < 32u;
 }
 
 // kExpMode = how many of every eight score pairs take their exponential on the FMA pipes (cubic polynomial,
@@ -406,66 +414,67 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
 
 
 // ---------------------------------------------------------------------------------------------------
-// 64-key tiles with double-buffered S and P in TMEM and register-prefetched scores.
+// Two query tiles per CTA (256 query rows), one CTA per SM, alternating exponent phases.
 //
-// tcgen05.ld moves 64 B/clk per SM: reading a 128 x 128 fp32 score tile out of TMEM costs as many cycles
-// (1024) as its exponentials on the MUFU pipe, so both have to overlap INSIDE each softmax warp.  With
-// 64-key tiles two S buffers and two P buffers fit in the CTA's 256 TMEM columns next to O:
+// Measured on the one-tile kernel above (SM-clock traces, tools/attn_trace.py): per key tile a softmax warp
+// spends ~1400 clk issuing its 128 MUFU.EX2 (+ the FFMA2/FADD2/F2FP woven in between) and ~900 clk on
+// everything else (TMEM load, row max, barrier round trips, P store).  The SM sub-partition's MUFU unit is
+// only kept busy when the two warps that share it (one per co-resident CTA) are in DIFFERENT phases -- and two
+// independent CTAs drift into the same phase and stay there (2250 vs 3450 clk per tile pair).  Here the two
+// query tiles live in ONE CTA, so the two warps of a sub-partition hand a token back and forth:
+// exps(tile 0, j) -> exps(tile 1, j) -> exps(tile 0, j+1) ...; each warp's other work runs under its
+// partner's exponentials.  K / V tiles are fetched once per 256 query rows.
 //
-//   TMEM  = S0 (64 fp32 cols) | S1 (64) | P0 (32 cols = 64 fp16) | P1 (32) | O (64)
-//   the MMA warp keeps Q K^T two tiles ahead of the softmax: S(j+1) is complete in TMEM while the softmax
-//   warps work on S(j), so they issue the (asynchronous) tcgen05.ld of S(j+1) first, run max / exp2 /
-//   row sum / fp16 packing on the registers of S(j) while the load streams in, store P(j) and go on.
-//
-//   grid  = (ceil(T/128) query tiles, heads, images), 2 CTAs co-resident per SM
-//   CTA   = 192 threads: warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 softmax (1 thread = 1 row)
-//   smem  = Q (16 KB) | K ring (8 KB tiles, released by Q K^T) | V ring (8 KB tiles, released by P V)
-constexpr int kKV3 = 64;
-constexpr int kAttn3Threads = 256;                // 2 warpgroups: {TMA, MMA, 2 idle} | 4 softmax warps
-constexpr int kRegs3Issue = 48, kRegs3Softmax = 208;  // 128 * (48 + 208) = half of the register file per CTA
-constexpr int kTile3Bytes = kKV3 * kHeadDim * 2;  // 8 KB
-constexpr uint32_t kCol3S = 0, kCol3P = 128, kCol3O = 192;
-constexpr int attn3_smem_bytes(int sk, int sv) { return kTileBytes + kTile3Bytes * (sk + sv) + 1024; }
+//   CTA   = 384 threads = 3 warpgroups: warp 0 TMA, warp 1 MMA issuer (warps 2-3 idle) | warps 4-7 softmax
+//           of query tile 0 | warps 8-11 softmax of query tile 1 (setmaxnreg 80 / 208 / 208)
+//   TMEM  = 512 columns: per query tile  S (128 fp32) | P (64 cols = 128 fp16) | O (64 fp32)
+//   MMA order per key tile j:  S0(j+1) = Q0 K(j+1)^T | O1 += P1(j-1) V(j-1) | S1(j+1) | O0 += P0(j) V(j)
+constexpr int kAttn2Threads = 384;
+constexpr int kRegs2Issue = 80, kRegs2Softmax = 208;  // 128 * (80 + 2 * 208) <= 64 K registers
+constexpr int attn2_smem_bytes(int sk, int sv) { return kTileBytes * (2 + sk + sv) + 1024; }
 
-template <int kExpMode, int kSK, int kSV, int kAb = 0>
-__global__ void __launch_bounds__(kAttn3Threads, 2)
-attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                 __half* __restrict__ out, int64_t ldo, int T, int D, float scale_log2) {
+template <int kPass, int kSK, int kSV, int kAb = 0>
+__global__ void __launch_bounds__(kAttn2Threads, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
+                 int T, int D, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + kTileBytes;                       // [kSK]
-  uint8_t* sV = smem + kTileBytes + kTile3Bytes * kSK;   // [kSV]
-  uint64_t* bars = reinterpret_cast<uint64_t*>((smem - smem_raw) >= kBarrierBytes
-                                                   ? smem_raw
-                                                   : smem + kTileBytes + kTile3Bytes * (kSK + kSV));
+  uint8_t* sQ = smem;                            // [2]
+  uint8_t* sK = smem + kTileBytes * 2;           // [kSK]
+  uint8_t* sV = smem + kTileBytes * (2 + kSK);   // [kSV]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((smem - smem_raw) >= kBarrierBytes ? smem_raw
+                                                                                  : smem + kTileBytes * (2 + kSK + kSV));
   uint64_t* q_full = bars;                 // 1
   uint64_t* k_full = bars + 1;             // [kSK]  TMA -> MMA
   uint64_t* v_full = k_full + kSK;         // [kSV]  TMA -> MMA
-  uint64_t* k_empty = v_full + kSV;        // [kSK]  MMA -> TMA : Q K_j^T complete
-  uint64_t* v_empty = k_empty + kSK;       // [kSV]  MMA -> TMA : P_j V_j complete
-  uint64_t* s_full = v_empty + kSV;        // [2]    MMA -> softmax : S_j complete in buffer j & 1
-  uint64_t* s_empty = s_full + 2;          // [2]    softmax -> MMA : S_j now in registers
-  uint64_t* p_full = s_empty + 2;          // [2]    softmax -> MMA : P_j in buffer j & 1 (and O rescaled)
-  uint64_t* pv_done = p_full + 2;          // [2]    MMA -> softmax : O += P_j V_j complete (j & 1)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-  static_assert((1 + 2 * kSK + 2 * kSV + 8) * 8 + 4 <= kBarrierBytes, "barrier area too small");
+  uint64_t* k_empty = v_full + kSV;        // [kSK]  MMA -> TMA : Q_t K_j^T complete for both query tiles
+  uint64_t* v_empty = k_empty + kSK;       // [kSV]  MMA -> TMA : P_t V_j complete for both query tiles
+  uint64_t* s_full = v_empty + kSV;        // [2]    MMA -> softmax t : S_t(j) complete
+  uint64_t* s_empty = s_full + 2;          // [2]    softmax t -> MMA : S_t(j) now in registers
+  uint64_t* p_full = s_empty + 2;          // [2]    softmax t -> MMA : P_t(j) in TMEM (and O_t rescaled)
+  uint64_t* pv_done = p_full + 2;          // [2]    MMA -> softmax t : O_t += P_t(j) V(j) complete
+  // MUFU token of each sub-partition.  (Plain shared-memory counters polled with volatile loads were tried
+  // instead of mbarriers: the hand-over is quicker, but the polling LDS share the MIO queue with the
+  // partner's MUFU.EX2 and the kernel gets 8 % slower.)
+  uint64_t* turn_a = pv_done + 2;          // [4]    tile-0 warp -> tile-1 warp of a sub-partition: exps(j) done
+  uint64_t* turn_b = turn_a + 4;           // [4]    tile-1 warp -> tile-0 warp: exps(j) done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn_b + 4);
+  static_assert((1 + 2 * kSK + 2 * kSV + 16) * 8 + 4 <= kBarrierBytes, "barrier area too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+  const int head = blockIdx.y, img = blockIdx.z;
   const int row0 = img * T;              // first token row of this image in the [B*T, 3D] matrix
-  const int q0 = q_tile * kBlockQ;
-  const int n_kv = (T + kKV3 - 1) / kKV3;
-  // real keys of the last tile, rounded up to the 16-column granularity of the MMAs
-  const int last_valid = T - (n_kv - 1) * kKV3;
+  const int q0 = blockIdx.x * (2 * kBlockQ);
+  const bool two = (q0 + kBlockQ < T);   // the last CTA of an image may hold a single query tile
+  const int n_kv = (T + kBlockKV - 1) / kBlockKV;
+  const int last_valid = T - (n_kv - 1) * kBlockKV;
   const int last_cols = (last_valid + 15) & ~15;
 
   griddep_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmKV);
+      tma_prefetch_desc(&tmQKV);
       mbar_init(q_full, 1);
       for (int s = 0; s < kSK; ++s) {
         mbar_init(&k_full[s], 1);
@@ -475,152 +484,221 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(&v_full[s], 1);
         mbar_init(&v_empty[s], 1);
       }
-      for (int b = 0; b < 2; ++b) {
-        mbar_init(&s_full[b], 1);
-        mbar_init(&s_empty[b], 4);
-        mbar_init(&p_full[b], 4);
-        mbar_init(&pv_done[b], 1);
+      for (int t = 0; t < 2; ++t) {
+        mbar_init(&s_full[t], 1);
+        mbar_init(&s_empty[t], 4);
+        mbar_init(&p_full[t], 4);
+        mbar_init(&pv_done[t], 1);
+      }
+      for (int q = 0; q < 4; ++q) {
+        mbar_init(&turn_a[q], 1);
+        mbar_init(&turn_b[q], 1);
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<kTmemCols>(tmem_slot);
+    tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();  // qkv of the preceding GEMM is complete and visible
+  constexpr bool kTrace = (kAb == 7);
+  uint32_t* trace = nullptr;
+  if constexpr (kTrace) {
+    const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (g_attn_trace != nullptr && lin >= 300 && (lin - 300) % 37 == 0 && (lin - 300) / 37 < kTraceCtas)
+      trace = g_attn_trace + ((lin - 300) / 37) * kTraceIters * kTraceEvents;
+  }
+  auto stamp = [&](int j, int ev, float dep) {
+    if constexpr (kTrace) {
+      if (trace != nullptr && j < kTraceIters) trace[j * kTraceEvents + ev] = clk_after(dep);
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs3Issue));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs2Issue));
     if (elect_one_sync()) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_2d(sQ, &tmQ, q_full, head * kHeadDim, row0 + q0);
+      mbar_arrive_expect_tx(q_full, two ? 2 * kTileBytes : kTileBytes);
+      tma_load_2d(sQ, &tmQKV, q_full, head * kHeadDim, row0 + q0);
+      if (two) tma_load_2d(sQ + kTileBytes, &tmQKV, q_full, head * kHeadDim, row0 + q0 + kBlockQ);
     }
     for (int j = 0; j < n_kv; ++j) {
       const int sk = j % kSK, sv = j % kSV;
       mbar_wait(&k_empty[sk], ((j / kSK) & 1u) ^ 1u);
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&k_full[sk], kTile3Bytes);
-        tma_load_2d(sK + sk * kTile3Bytes, &tmKV, &k_full[sk], D + head * kHeadDim, row0 + j * kKV3);
+        mbar_arrive_expect_tx(&k_full[sk], kTileBytes);
+        tma_load_2d(sK + sk * kTileBytes, &tmQKV, &k_full[sk], D + head * kHeadDim, row0 + j * kBlockKV);
       }
       mbar_wait(&v_empty[sv], ((j / kSV) & 1u) ^ 1u);
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&v_full[sv], kTile3Bytes);
-        tma_load_2d(sV + sv * kTile3Bytes, &tmKV, &v_full[sv], 2 * D + head * kHeadDim, row0 + j * kKV3);
+        mbar_arrive_expect_tx(&v_full[sv], kTileBytes);
+        tma_load_2d(sV + sv * kTileBytes, &tmQKV, &v_full[sv], 2 * D + head * kHeadDim, row0 + j * kBlockKV);
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs3Issue));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs2Issue));
     constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, false, true);  // B (V) is MN-major
-    const uint64_t q_desc = make_sw128_desc(smem_u32(sQ), 16, 1024);
-    const uint32_t t_o = tmem_base + kCol3O;
-
-    auto issue_qk = [&](int j) {  // S_j -> buffer j & 1
+    // S_t(j) = Q_t K_j^T; `release_k`: last reader of the K stage
+    auto issue_qk = [&](int j, int t, bool release_k) {
       const int s = j % kSK;
-      const int ncols = (j == n_kv - 1) ? last_cols : kKV3;
+      const int ncols = (j == n_kv - 1) ? last_cols : kBlockKV;
       const uint32_t idesc_qk = make_idesc_f16(128, ncols, false, false);
-      mbar_wait(&k_full[s], (j / kSK) & 1u);
-      tc_fence_after();
-      const uint64_t k_desc = make_sw128_desc(smem_u32(sK + s * kTile3Bytes), 16, 1024);
-      const uint32_t t_s = tmem_base + kCol3S + (j & 1) * kKV3;
+      const uint64_t q_desc = make_sw128_desc(smem_u32(sQ + t * kTileBytes), 16, 1024);
+      const uint64_t k_desc = make_sw128_desc(smem_u32(sK + s * kTileBytes), 16, 1024);
+      const uint32_t t_s = tmem_base + t * 256 + kColS;
       if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k)
           umma_f16_ss(t_s, q_desc + 2u * k, k_desc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
-        umma_commit(&k_empty[s]);
-        umma_commit(&s_full[j & 1]);
+        if (release_k) umma_commit(&k_empty[s]);
+        umma_commit(&s_full[t]);
+      }
+      __syncwarp();
+    };
+    // O_t += P_t(j) V_j; `release_v`: last reader of the V stage
+    auto issue_pv = [&](int j, int t, bool release_v) {
+      const int s = j % kSV;
+      // V tile: 128 keys (K) x 64 dims (N), N contiguous: MN-major, 8-key groups 1024 B apart.
+      const uint64_t v_desc = make_sw128_desc(smem_u32(sV + s * kTileBytes), 1024, 1024);
+      const uint32_t t_p = tmem_base + t * 256 + kColP;
+      const uint32_t t_o = tmem_base + t * 256 + kColO;
+      const int ksteps = ((j == n_kv - 1) ? last_cols : kBlockKV) / 16;
+      if (elect_one_sync()) {
+        for (int k = 0; k < ksteps; ++k)  // A: 8 TMEM columns of P per K step; B: 16 keys = 2048 B per K step
+          umma_f16_ts(t_o, t_p + 8u * k, v_desc + 128u * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        if (release_v) umma_commit(&v_empty[s]);
+        umma_commit(&pv_done[t]);
       }
       __syncwarp();
     };
 
     mbar_wait(q_full, 0);
-    issue_qk(0);
-    if (n_kv > 1) issue_qk(1);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0, !two);
+    if (two) issue_qk(0, 1, true);
     for (int j = 0; j < n_kv; ++j) {
-      if (j >= 1 && j + 1 < n_kv) {
-        // buffer (j+1) & 1 held S_{j-1}: free once the softmax warps have it in registers
-        mbar_wait(&s_empty[(j + 1) & 1], ((j - 1) >> 1) & 1u);
+      if (j + 1 < n_kv) {
+        mbar_wait(&s_empty[0], j & 1u);  // softmax 0 holds S_0(j) in registers
+        mbar_wait(&k_full[(j + 1) % kSK], ((j + 1) / kSK) & 1u);
         tc_fence_after();
-        issue_qk(j + 1);
+        issue_qk(j + 1, 0, !two);
       }
-      const int s = j % kSV;
-      mbar_wait(&v_full[s], (j / kSV) & 1u);
-      mbar_wait(&p_full[j & 1], (j >> 1) & 1u);
+      if (two && j >= 1) {
+        mbar_wait(&p_full[1], (j - 1) & 1u);
+        tc_fence_after();
+        issue_pv(j - 1, 1, true);
+      }
+      if (two && j + 1 < n_kv) {
+        mbar_wait(&s_empty[1], j & 1u);
+        tc_fence_after();
+        issue_qk(j + 1, 1, true);
+      }
+      mbar_wait(&v_full[j % kSV], (j / kSV) & 1u);
+      mbar_wait(&p_full[0], j & 1u);
       tc_fence_after();
-      // V tile: 64 keys (K) x 64 dims (N), N contiguous: MN-major, 8-key groups 1024 B apart.
-      const uint64_t v_desc = make_sw128_desc(smem_u32(sV + s * kTile3Bytes), 1024, 1024);
-      const uint32_t t_p = tmem_base + kCol3P + (j & 1) * (kKV3 / 2);
-      const int ksteps = ((j == n_kv - 1) ? last_cols : kKV3) / 16;
-      if (elect_one_sync()) {
-        for (int k = 0; k < ksteps; ++k) {
-          // A: 16 fp16 of P = 8 TMEM columns per K step; B: 16 keys = 2048 B per K step
-          umma_f16_ts(t_o, t_p + 8u * k, v_desc + 128u * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&v_empty[s]);
-        umma_commit(&pv_done[j & 1]);
-      }
-      __syncwarp();
+      issue_pv(j, 0, !two);
+    }
+    if (two) {
+      mbar_wait(&p_full[1], (n_kv - 1) & 1u);
+      tc_fence_after();
+      issue_pv(n_kv - 1, 1, true);
     }
   } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs3Issue));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs2Issue));
   } else {
     // ------------------------------ Softmax warps ------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs3Softmax));
-    const int sub = warp & 3;             // TMEM sub-partition (lane quarter) of this warp
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs2Softmax));
+    const int t = (warp - 4) >> 2;        // query tile of this warp
+    const int sub = warp & 3;             // TMEM sub-partition (lane quarter) = SM sub-partition of this warp
     const int row = sub * 32 + lane;
+    const int qt0 = q0 + t * kBlockQ;
     const uint32_t lane_base = static_cast<uint32_t>(sub * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_base + kCol3S;
-    const uint32_t t_p = tmem_base + lane_base + kCol3P;
-    const uint32_t t_o = tmem_base + lane_base + kCol3O;
-    const bool warp_has_rows = (q0 + sub * 32) < T;  // warp-uniform
+    const uint32_t t_s = tmem_base + lane_base + t * 256 + kColS;
+    const uint32_t t_p = tmem_base + lane_base + t * 256 + kColP;
+    const uint32_t t_o = tmem_base + lane_base + t * 256 + kColO;
+    uint64_t* my_s_full = &s_full[t];
+    uint64_t* my_s_empty = &s_empty[t];
+    uint64_t* my_p_full = &p_full[t];
+    uint64_t* my_pv_done = &pv_done[t];
+    uint64_t* turn_wait = (t == 0) ? &turn_b[sub] : &turn_a[sub];
+    uint64_t* turn_pass = (t == 0) ? &turn_a[sub] : &turn_b[sub];
+    const bool warp_has_rows = (qt0 + sub * 32) < T;  // warp-uniform
+    // exps(tile 0, j) waits for exps(tile 1, j-1); exps(tile 1, j) waits for exps(tile 0, j)
+    auto take_turn = [&](int j) {
+      if (two) {
+        if (t == 0) {
+          if (j > 0) mbar_wait(turn_wait, (j - 1) & 1u);
+        } else {
+          mbar_wait(turn_wait, j & 1u);
+        }
+      }
+    };
+    auto pass_turn = [&](int) {
+      if (two) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(turn_pass);
+      }
+    };
 
-    if (!warp_has_rows) {
+    if (t == 1 && !two) {
+      // no second query tile in this CTA
+    } else if (!warp_has_rows) {
       // All 32 rows of this warp are beyond the sequence: their S/P/O lanes hold garbage that is never
       // stored and never mixes with other rows (the MMAs are row-independent); keep the protocol alive.
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&s_full[j & 1], (j >> 1) & 1u);
+        mbar_wait(my_s_full, j & 1u);
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_empty[j & 1]);
-          mbar_arrive(&p_full[j & 1]);
-        }
+        if (lane == 0) mbar_arrive(my_s_empty);
+        take_turn(j);
+        pass_turn(j);
+        // arrive on p_full(j) only once phase j-1 is over (P V(j-1) complete implies it): this warp runs
+        // ahead of the warps that do have rows, and an early arrival would complete THEIR pending phase
+        if (j > 0) mbar_wait(my_pv_done, (j - 1) & 1u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(my_p_full);
       }
+      mbar_wait(my_pv_done, (n_kv - 1) & 1u);
     } else {
       float m_used = -INFINITY;  // running max (log2 domain) actually used as the exponent offset
       float l = 0.0f;
-      uint32_t sA[2][32], sB[2][32];
 
-      // One 64-key tile of the online softmax.  `cur` holds S_j; the load of S_{j+1} into `nxt` is issued
-      // first and only waited for at the end, so it streams out of TMEM underneath the exponentials.
-      auto process = [&](uint32_t (&cur)[2][32], uint32_t (&nxt)[2][32], int j) {
-        const int b = j & 1;
-        const bool more = (j + 1 < n_kv);
-        if (more) {
-          mbar_wait(&s_full[b ^ 1], ((j + 1) >> 1) & 1u);
-          tc_fence_after();
-          tmem_ld_32x32(t_s + (b ^ 1) * kKV3, nxt[0]);
-          tmem_ld_32x32(t_s + (b ^ 1) * kKV3 + 32, nxt[1]);
-        }
-        if (j == n_kv - 1) {  // keys beyond T (or rows of the next image): -inf
+      const bool tracer = kTrace && sub == 0 && lane == 0;
+      // One key tile.  On entry S_t(j) is complete in TMEM (the wait for it happened at the end of tile j-1).
+      // The exponentials are issued as ONE uninterrupted run of MUFU.EX2 between take_turn and pass_turn; the
+      // scale-and-shift before and the row sum / fp16 packing after run under the partner warp's run.
+      auto softmax_tile = [&](auto nch_c, auto last_c, int j) {
+        constexpr int NCH = decltype(nch_c)::value;
+        constexpr bool kLast = decltype(last_c)::value;  // static: the key mask costs 2 instructions per score
+        uint32_t s[NCH][32];
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(my_s_empty);
+        if (tracer) stamp(j, t * 8 + 0, __uint_as_float(s[0][0]));
+
+        if constexpr (kLast) {  // keys beyond T (or rows of the next image): -inf
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
 #pragma unroll
             for (int k = 0; k < 32; ++k)
-              if (c * 32 + k >= last_valid) cur[c][k] = 0xff800000u;
+              if (c * 32 + k >= last_valid) s[c][k] = 0xff800000u;
         }
         // row max: independent chains (3-input max), then combine
         float mx = -INFINITY;
-        if constexpr (kAb == 4) mx = fmaxf(__uint_as_float(cur[0][0]), __uint_as_float(cur[0][1]));
+        if constexpr (kAb == 4) mx = fmaxf(__uint_as_float(s[0][0]), __uint_as_float(s[0][1]));
 #pragma unroll
-        for (int c = 0; c < (kAb == 4 ? 0 : 2); ++c) {
-          float m0 = fmaxf(__uint_as_float(cur[c][0]), __uint_as_float(cur[c][1]));
+        for (int c = 0; c < (kAb == 4 ? 0 : NCH); ++c) {
+          float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
 #pragma unroll
           for (int k = 2; k < 32; k += 2)
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[c][k]), __uint_as_float(cur[c][k + 1])));
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][k]), __uint_as_float(s[c][k + 1])));
           mx = fmaxf(mx, m0);
         }
         const float m_new = fmaxf(m_used, mx * scale_log2);
@@ -630,23 +708,57 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           alpha = exp2f(m_used - m_new);  // 0 on the first tile
           m_used = m_new;
         }
-        // exponentials (MUFU.EX2), packed f32x2 FMA/ADD, two accumulator pairs
+        // (A) exponent arguments, in place
         const float2 sc2 = make_float2(scale_log2, scale_log2);
         const float2 nm2 = make_float2(-m_used, -m_used);
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-        uint32_t p[2][16];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(s[c][k]), __uint_as_float(s[c][k + 1])), sc2, nm2);
+            s[c][k] = __float_as_uint(a.x);
+            s[c][k + 1] = __float_as_uint(a.y);
+          }
+#pragma unroll
+          for (int k = 0; k < 32; k += 16)  // pin: the arguments exist before the token is requested
+            asm volatile("" : "+r"(s[c][k]), "+r"(s[c][k + 1]), "+r"(s[c][k + 2]), "+r"(s[c][k + 3]), "+r"(s[c][k + 4]),
+                              "+r"(s[c][k + 5]), "+r"(s[c][k + 6]), "+r"(s[c][k + 7]), "+r"(s[c][k + 8]), "+r"(s[c][k + 9]),
+                              "+r"(s[c][k + 10]), "+r"(s[c][k + 11]), "+r"(s[c][k + 12]), "+r"(s[c][k + 13]),
+                              "+r"(s[c][k + 14]), "+r"(s[c][k + 15]));
+        }
+        if (tracer) stamp(j, t * 8 + 1, 0.f);
+        // (B) this warp's turn on the MUFU pipe of its sub-partition
+        take_turn(j);
+        if (tracer) stamp(j, t * 8 + 2, 0.f);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            if constexpr (kAb != 1 && kAb != 4) {
+              float e;
+              asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(s[c][k])));
+              s[c][k] = __float_as_uint(e);
+            }
+            // hand the token on kPass exponentials into the run (full tiles; at the end of a short last tile):
+            // the partner needs ~350 clk from this arrive to its first MUFU
+            if ((NCH == 4 && c * 32 + k + 1 == kPass) || (NCH < 4 && c == NCH - 1 && k == 31)) {
+              if (opaque_true()) pass_turn(j);
+            }
+          }
+          // hand the token on a little before the end of the run: the partner needs ~150 clk to wake up
+          // (its first exponentials then overlap this warp's last sixteen)
+        }
+        if (tracer) stamp(j, t * 8 + 3, __uint_as_float(s[NCH - 1][31]));
+        // (C) row sum and fp16 packing -- in a block of its own, so that it is not woven into the MUFU run
+        if (!opaque_true()) return;
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        uint32_t p[NCH][16];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
-            if constexpr (kAb == 4) { p[c][k / 2] = cur[c][k]; p[c][k / 2 + 1] = cur[c][k + 2]; continue; }
-            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(cur[c][k]), __uint_as_float(cur[c][k + 1])), sc2, nm2);
-            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(cur[c][k + 2]), __uint_as_float(cur[c][k + 3])), sc2, nm2);
-            const int pair = (k >> 1) & 7;  // pair index within a group of 8 pairs
-            const bool poly0 = (kExpMode >= 1 && pair == 0) || (kExpMode >= 2 && pair == 4);
-            const bool poly1 = (kExpMode >= 3) && (pair + 1 == 3);
-            const float2 e0 = (kAb == 1) ? t0 : poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
-            const float2 e1 = (kAb == 1) ? t1 : poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
+            const float2 e0 = make_float2(__uint_as_float(s[c][k]), __uint_as_float(s[c][k + 1]));
+            const float2 e1 = make_float2(__uint_as_float(s[c][k + 2]), __uint_as_float(s[c][k + 3]));
             acc0 = __fadd2_rn(acc0, e0);
             acc1 = __fadd2_rn(acc1, e1);
             const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
@@ -655,54 +767,53 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
         l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
+        if (tracer) stamp(j, t * 8 + 4, l);
 
-        if (j >= 2) mbar_wait(&pv_done[b], ((j >> 1) - 1) & 1u);  // P V_{j-2} complete: P buffer b is free
-        if (j >= 1 && __any_sync(0xffffffffu, rescale)) {           // rare after the first tiles
-          mbar_wait(&pv_done[b ^ 1], ((j - 1) >> 1) & 1u);          // P V_{j-1} complete: O is stable
-          tc_fence_after();
+        // S_t(j+1) complete also means P V(j-1) complete (the MMA warp issues it earlier): the P buffer is
+        // free and O is stable.  One wait serves both, and tile j+1 starts without waiting.
+        if (j + 1 < n_kv) {
+          mbar_wait(my_s_full, (j + 1) & 1u);
+        } else if (j > 0) {
+          mbar_wait(my_pv_done, (j - 1) & 1u);
+        }
+        tc_fence_after();
+        if (tracer) stamp(j, t * 8 + 5, 0.f);
+        if (j > 0 && __any_sync(0xffffffffu, rescale)) {  // rare after the first tiles: small chunks
 #pragma unroll 1
           for (int c = 0; c < kHeadDim / 8; ++c) {
             uint32_t o[8];
             tmem_ld_32x8(t_o + c * 8, o);
-            tmem_ld_wait();  // (also completes the S prefetch: harmless, this path is rare)
+            tmem_ld_wait();
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
             tmem_st_32x8(t_o + c * 8, o);
           }
         }
-        tc_fence_after();
-        tmem_st_32x16(t_p + b * (kKV3 / 2), p[0]);
-        tmem_st_32x16(t_p + b * (kKV3 / 2) + 16, p[1]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tmem_st_32x16(t_p + c * 16, p[c]);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[b]);
-        if (more) {
-          tmem_ld_wait();  // S_{j+1} is in registers: its TMEM buffer may be overwritten by Q K_{j+3}^T
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[b ^ 1]);
-        }
+        if (lane == 0) mbar_arrive(my_p_full);
+        if (tracer) stamp(j, t * 8 + 6, 0.f);
       };
 
-      mbar_wait(&s_full[0], 0);
+      mbar_wait(my_s_full, 0);
       tc_fence_after();
-      tmem_ld_32x32(t_s, sA[0]);
-      tmem_ld_32x32(t_s + 32, sA[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[0]);
-      for (int j = 0; j < n_kv; j += 2) {
-        process(sA, sB, j);
-        if (j + 1 < n_kv) process(sB, sA, j + 1);
+      const int last_nch = (last_cols + 31) >> 5;  // 32-column chunks of the last tile that hold real keys
+      for (int j = 0; j < n_kv - 1; ++j) softmax_tile(std::integral_constant<int, 4>{}, std::false_type{}, j);
+      switch (last_nch) {
+        case 1: softmax_tile(std::integral_constant<int, 1>{}, std::true_type{}, n_kv - 1); break;
+        case 2: softmax_tile(std::integral_constant<int, 2>{}, std::true_type{}, n_kv - 1); break;
+        case 3: softmax_tile(std::integral_constant<int, 3>{}, std::true_type{}, n_kv - 1); break;
+        default: softmax_tile(std::integral_constant<int, 4>{}, std::true_type{}, n_kv - 1); break;
       }
 
       // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
-      mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1u);
+      mbar_wait(my_pv_done, (n_kv - 1) & 1u);
       tc_fence_after();
       const float inv_l = 1.0f / l;
-      const int q = q0 + row;
+      const int q = qt0 + row;
       __half* dst = out + static_cast<int64_t>(row0 + q) * ldo + head * kHeadDim;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -731,19 +842,18 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
 int g_attn_exp_mode = -1;  // -1: not chosen yet (MHMR_ATTN_EXP, else kDefaultExpMode)
 constexpr int kDefaultExpMode = 0;
 int g_attn_stages = -1;    // 10 * K stages + V stages (MHMR_ATTN_STAGES, else kDefaultStages)
-constexpr int kDefaultStages = 33;
+constexpr int kDefaultStages = 244;
 int g_attn_ablate = -1;    // MHMR_ATTN_ABLATE: timing experiments only (wrong results), see tools/attn_ablate.py
 
 struct AttnArgs {
   CUtensorMap tm;     // 128-row boxes (Q; K and V of the 128-key kernel)
-  CUtensorMap tm_kv;  // 64-row boxes (K and V of the 64-key kernel)
   __half* out;
   int64_t ldo;
   int T, D;
@@ -782,18 +892,18 @@ int attn_launch(const AttnArgs& a) {
   return MHMR_OK;
 }
 
-template <int kExpMode, int kSK, int kSV, int kAb>
-int attn3_launch(const AttnArgs& a) {
-  constexpr int smem = attn3_smem_bytes(kSK, kSV);
-  auto kern = attn_fwd3_kernel<kExpMode, kSK, kSV, kAb>;
+template <int kPass, int kSK, int kSV, int kAb>
+int attn2_launch(const AttnArgs& a) {
+  constexpr int smem = attn2_smem_bytes(kSK, kSV);
+  auto kern = attn_fwd2_kernel<kPass, kSK, kSV, kAb>;
   static bool attr_set = false;
   if (!attr_set) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = a.grid;
-  cfg.blockDim = dim3(kAttn3Threads);
+  cfg.gridDim = dim3((a.grid.x + 1) / 2, a.grid.y, a.grid.z);
+  cfg.blockDim = dim3(kAttn2Threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = a.stream;
   cudaLaunchAttribute attr[1];
@@ -801,20 +911,30 @@ int attn3_launch(const AttnArgs& a) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.tm, a.tm_kv, a.out, a.ldo, a.T, a.D, a.scale_log2));
+  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.tm, a.out, a.ldo, a.T, a.D, a.scale_log2));
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }
 
+int g_attn_pass = -1;  // MHMR_ATTN_PASS: exponentials issued before the MUFU token is handed on
+
 template <int kSK, int kSV>
-int attn3_dispatch(const AttnArgs& a, int exp_mode, int ablate) {
-  if (ablate == 1) return attn3_launch<0, kSK, kSV, 1>(a);
-  if (ablate == 4) return attn3_launch<0, kSK, kSV, 4>(a);
-  switch (exp_mode) {
-    case 1: return attn3_launch<1, kSK, kSV, 0>(a);
-    case 2: return attn3_launch<2, kSK, kSV, 0>(a);
-    case 3: return attn3_launch<3, kSK, kSV, 0>(a);
-    default: return attn3_launch<0, kSK, kSV, 0>(a);
+int attn2_dispatch(const AttnArgs& a, int /*exp_mode*/, int ablate) {
+  if (g_attn_pass < 0) {
+    const char* e = std::getenv("MHMR_ATTN_PASS");
+    g_attn_pass = (e != nullptr) ? atoi(e) : 112;
+  }
+  if (ablate == 7) return attn2_launch<64, kSK, kSV, 7>(a);
+  if (ablate == 1) return attn2_launch<64, kSK, kSV, 1>(a);
+  if (ablate == 4) return attn2_launch<64, kSK, kSV, 4>(a);
+  switch (g_attn_pass) {
+    case 32: return attn2_launch<32, kSK, kSV, 0>(a);
+    case 48: return attn2_launch<48, kSK, kSV, 0>(a);
+    case 80: return attn2_launch<80, kSK, kSV, 0>(a);
+    case 96: return attn2_launch<96, kSK, kSV, 0>(a);
+    case 64: return attn2_launch<64, kSK, kSV, 0>(a);
+    case 128: return attn2_launch<128, kSK, kSV, 0>(a);
+    default: return attn2_launch<112, kSK, kSV, 0>(a);
   }
 }
 
@@ -847,9 +967,6 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   int rc = make_tmap_2d(&a.tm, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<uint64_t>(B) * T,
                         3ull * D, ld_qkv * 2, 128, 64, true);
   if (rc != MHMR_OK) return rc;
-  rc = make_tmap_2d(&a.tm_kv, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<uint64_t>(B) * T, 3ull * D,
-                    ld_qkv * 2, kKV3, 64, true);
-  if (rc != MHMR_OK) return rc;
   if (g_attn_exp_mode < 0) {
     const char* e = std::getenv("MHMR_ATTN_EXP");
     g_attn_exp_mode = (e != nullptr && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : kDefaultExpMode;
@@ -874,7 +991,8 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
     MHMR_CUDA_CHECK(cudaMalloc(&d_trace, trace_words * 4));
     MHMR_CUDA_CHECK(cudaMemset(d_trace, 0, trace_words * 4));
     MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &d_trace, sizeof(d_trace)));
-    rc = attn_dispatch<3, 3>(a, g_attn_exp_mode, g_attn_ablate);
+    rc = (g_attn_stages == 244) ? attn2_dispatch<4, 4>(a, g_attn_exp_mode, g_attn_ablate)
+                                : attn_dispatch<3, 3>(a, g_attn_exp_mode, g_attn_ablate);
     if (rc != MHMR_OK) return rc;
     MHMR_CUDA_CHECK(cudaStreamSynchronize(stream));
     std::vector<uint32_t> h(trace_words);
@@ -889,8 +1007,8 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
     return MHMR_OK;
   }
   switch (g_attn_stages) {
-    case 344: return attn3_dispatch<4, 4>(a, g_attn_exp_mode, g_attn_ablate);
-    case 355: return attn3_dispatch<5, 5>(a, g_attn_exp_mode, g_attn_ablate);
+    case 233: return attn2_dispatch<3, 3>(a, g_attn_exp_mode, g_attn_ablate);
+    case 244: return attn2_dispatch<4, 4>(a, g_attn_exp_mode, g_attn_ablate);
     case 22: return attn_dispatch<2, 2>(a, g_attn_exp_mode, g_attn_ablate);
     case 32: return attn_dispatch<3, 2>(a, g_attn_exp_mode, g_attn_ablate);
     case 23: return attn_dispatch<2, 3>(a, g_attn_exp_mode, g_attn_ablate);

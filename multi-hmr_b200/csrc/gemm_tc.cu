@@ -84,49 +84,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
+    // (whole warp on the warp-uniform loop, one elected lane issues -- see elect_one_sync)
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, false, false);
-      uint32_t stage = 0, phase = 0, acc_iter = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_iter) {
-        const uint32_t as = acc_iter & 1u;
-        const uint32_t aphase = (acc_iter >> 1) & 1u;
-        mbar_wait(&tempty_bar[as], aphase ^ 1u);  // epilogue has drained this accumulator
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN, false, false);
+    uint32_t stage = 0, phase = 0, acc_iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_iter) {
+      const uint32_t as = acc_iter & 1u;
+      const uint32_t aphase = (acc_iter >> 1) & 1u;
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t a_desc = make_sw128_desc(sa, 16, 1024);
-          const uint64_t b_desc = make_sw128_desc(sb, 16, 1024);
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+        const uint64_t a_desc = make_sw128_desc(sa, 16, 1024);
+        const uint64_t b_desc = make_sw128_desc(sb, 16, 1024);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance K by 16 fp16 = 32 B inside the 128-B swizzle row: +2 in (addr >> 4) units
-            umma_f16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                       // smem slot free once MMAs retire
           if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);    // accumulator complete
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {

@@ -144,27 +144,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
-        const int m0 = m_blk * BM2 + static_cast<int>(rank) * 128;
-        const int n0 = n_blk * BN2 + static_cast<int>(rank) * (BN2 / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem + stage * kStageBytes2;
-          uint8_t* sb = sa + kABytes2;
+    // The whole warp runs the (warp-uniform) loop and one elected lane issues: under `if (lane == 0)` the
+    // compiler wraps every TMA / MMA / commit in an elect-and-retry loop (~80 clk each), see elect_one_sync.
+    uint32_t stage = 0, phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int m0 = m_blk * BM2 + static_cast<int>(rank) * 128;
+      const int n0 = n_blk * BN2 + static_cast<int>(rank) * (BN2 / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * kStageBytes2;
+        uint8_t* sb = sa + kABytes2;
+        if (elect_one_sync()) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes2);
           else mbar_arrive_leader(&full_bar[stage]);
           tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK2, m0);
           tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK2, n0);
-          if (++stage == kStages2) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == kStages2) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader only) ------------------
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_f16(BM2, BN2, false, false);
       uint32_t stage = 0, phase = 0, acc_iter = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++acc_iter) {
@@ -180,11 +183,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sb = sa + kABytes2;
           const uint64_t a_desc = make_sw128_desc(sa, 16, 1024);
           const uint64_t b_desc = make_sw128_desc(sb, 16, 1024);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK2 / 16; ++k)
-            umma_f16_ss_2cta(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_2cta(&empty_bar[stage]);                     // smem stage free in both CTAs
-          if (kb == num_kb - 1) umma_commit_2cta(&tfull_bar[as]);  // accumulator complete in both CTAs
+            for (int k = 0; k < BK2 / 16; ++k)
+              umma_f16_ss_2cta(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[stage]);                     // smem stage free in both CTAs
+            if (kb == num_kb - 1) umma_commit_2cta(&tfull_bar[as]);  // accumulator complete in both CTAs
+          }
+          __syncwarp();
           if (++stage == kStages2) { stage = 0; phase ^= 1u; }
         }
       }

@@ -21,11 +21,8 @@ print(json.dumps(dict(ms=round(ms, 4), tflops=round(4.0 * B * T * T * D / ms / 1
 ''' % (ROOT, ROOT)
 
 res = []
-envs = []
-for st in ("33", "344", "355"):
-    envs += [dict(MHMR_ATTN_STAGES=st), dict(MHMR_ATTN_STAGES=st, MHMR_ATTN_ABLATE="1"),
-             dict(MHMR_ATTN_STAGES=st, MHMR_ATTN_ABLATE="4")]
-envs += [dict(MHMR_ATTN_STAGES="344", MHMR_ATTN_EXP=str(m)) for m in (1, 2, 3)]
+envs = [dict(MHMR_ATTN_STAGES="33")]
+envs += [dict(MHMR_ATTN_STAGES="244", MHMR_ATTN_PASS=str(m)) for m in (96, 112, 128)]
 for env in envs:
     e = dict(os.environ, MHMR_ATTN_VERBOSE="1")
     e.update(env)
