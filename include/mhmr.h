@@ -58,11 +58,6 @@ int mhmr_op_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int
 int mhmr_op_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int B, int T, int D,
                       void* stream);
 
-/* Softmax exponentials of mhmr_op_attention / the engine: `mode` of every eight score pairs (0..3) are
- * evaluated on the FMA pipes with a cubic polynomial (relative error 7.5e-5, below the fp16 rounding of P),
- * the rest on MUFU.EX2.  0 = all MUFU (default). */
-int mhmr_set_attention_exp_mode(int mode);
-
 /* ------------------------------------------------------------------------------------------------
  * Engine: the whole `Model.forward(x, K)` path (reference model.py:205-349) behind one handle
  * ---------------------------------------------------------------------------------------------- */

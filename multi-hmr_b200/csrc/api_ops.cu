@@ -35,10 +35,4 @@ int mhmr_op_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, i
                            D, static_cast<cudaStream_t>(stream));
 }
 
-int mhmr_set_attention_exp_mode(int mode) {
-  MHMR_REQUIRE(mode >= 0 && mode <= 3, "attention mode: number of score pairs per eight on the FMA pipes, 0..3");
-  attention_set_exp_mode(mode);
-  return MHMR_OK;
-}
-
 }  // extern "C"

@@ -3,24 +3,45 @@
 // Replaces `softmax(q k^T / 8) v` of dinov2 `Attention.forward` (reached from the reference at
 // blocks/dinov2.py:25).  Flash-style: the T x T score matrix never leaves the SM.
 //
-//   grid  = (ceil(T/128) query tiles, heads, images), 2 CTAs co-resident per SM
-//   CTA   = 192 threads: warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 softmax (1 thread = 1 row)
-//   TMEM  = 256 columns: S (128 fp32) | P (64 cols = 128 fp16, A operand of the PV MMA) | O (64 fp32)
-//   S = Q K^T : tcgen05.mma SS, M=128 N=128 K=64     (K tile K-major,  128B swizzle, via TMA)
-//   O += P V  : tcgen05.mma TS, M=128 N=64  K=128    (V tile MN-major, 128B swizzle, via TMA)
+//   grid  = (ceil(T/256) query-tile pairs, heads, images), one CTA per SM
+//   CTA   = 384 threads = 3 warpgroups: warp 0 TMA, warp 1 MMA issuer (warps 2-3 idle) | warps 4-7 softmax
+//           of query tile 0 | warps 8-11 softmax of query tile 1 (1 thread = 1 query row; setmaxnreg
+//           80 / 208 / 208 registers)
+//   TMEM  = 512 columns: per query tile  S (128 fp32) | P (64 cols = 128 fp16, A operand of P V) | O (64 fp32)
+//   smem  = Q (2 x 16 KB) | K ring | V ring (16 KB tiles of 128 keys, 128B swizzle, one TMA each)
+//   S = Q K^T : tcgen05.mma SS, M=128 N=128 K=64     (K tile K-major)
+//   O += P V  : tcgen05.mma TS, M=128 N=64  K=128    (V tile MN-major)
+//   MMA order per key tile j:  S0(j+1) = Q0 K(j+1)^T | O1 += P1(j-1) V(j-1) | S1(j+1) | O0 += P0(j) V(j)
 // Online softmax in fp32 in the exp2 domain (packed f32x2 FMA/ADD, 3-input max) with lazy rescaling of O
-// (only when the running max grows by more than 2^8), so the O read-modify-write through tcgen05.ld/st
-// is rare.  The binding pipe is MUFU.EX2 (16/clk/SM): one exponential per score against 512 tensor cycles
-// per 128x128 tile.
+// (only when the running max grows by more than 2^8), so the O read-modify-write through tcgen05.ld/st is rare.
+//
+// What bounds it (SM-clock traces of the protocol events, tools/attn_trace.py, profiles/r01d_attention_timeline.md):
+// per key tile a softmax warp needs >= 1024 clk of MUFU.EX2 issue (128 exponentials, 4 lanes/clk per SM
+// sub-partition) and ~1100 clk of everything else (TMEM load, row max, scale-and-shift, row sum, fp16 packing,
+// P store, barrier round trips).  The MUFU unit of a sub-partition is only kept busy when the two warps that
+// share it are in DIFFERENT phases.  Two independent co-resident CTAs (the first design) drift into the same
+// phase and stay there (2250 clk per tile pair in anti-phase, 3450 clk in phase).  Here both query tiles live in
+// ONE CTA and the two warps of a sub-partition hand a token back and forth:
+//   exps(tile 0, j) -> exps(tile 1, j) -> exps(tile 0, j+1) ...
+// The exponentials are issued as one uninterrupted MUFU run (a branch keeps ptxas from weaving other work
+// into it); everything else runs under the partner's run.  K / V tiles are fetched once per 256 query rows.
+//
+// Issue warps run the whole warp on uniform control flow and elect one lane per issue (elect_one_sync): under
+// `if (lane == 0)` every TMA / MMA / commit costs ~80 clk in an elect-and-retry loop.
 //
 // Ragged sequence (T = N + 1 is 1 mod 128 for every Multi-HMR resolution):
 //   * the last key tile only computes the 16-column groups that hold real keys (QK^T with N = 16..128,
 //     PV with K = 16..128, softmax over the needed 32-column chunks);
-//   * softmax warps whose 32 query rows are all beyond T only keep the barrier protocol alive.
+//   * softmax warps whose 32 query rows are all beyond T only keep the barrier protocol alive;
+//   * the last CTA of an image holds a single query tile when ceil(T/128) is odd.
+//
+// Diagnostics (never on the product path): MHMR_ATTN_ABLATE=1 (no exponentials) / 4 (protocol only) time the
+// kernel with parts of the softmax removed (wrong results); MHMR_ATTN_ABLATE=7 MHMR_ATTN_TRACE=<file> dumps the
+// SM-clock timeline of a few CTAs.
 #include <cstdio>
 #include <cstdlib>
-#include <vector>
 #include <type_traits>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -31,51 +52,15 @@ namespace {
 constexpr int kHeadDim = 64;
 constexpr int kBlockQ = 128;
 constexpr int kBlockKV = 128;
-constexpr int kAttnThreads = 192;
 constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: Q, K or V tile
-constexpr int kBarrierBytes = 512;  // mbarriers + the TMEM slot
-// Q tile + K ring + V ring + 1 KB that covers both the 1024-byte alignment of the tiles and the barriers
-// (in front of the tiles when the alignment pad leaves room, behind them otherwise).  With 3 + 3 stages
-// this is 115712 B: exactly two CTAs per SM ((115712 + 1024 reserved) * 2 = 228 KB).
-constexpr int attn_smem_bytes(int sk, int sv) { return kTileBytes * (1 + sk + sv) + 1024; }
+constexpr int kBarrierBytes = 512;              // mbarriers + the TMEM slot
+constexpr int kStagesK = 4, kStagesV = 4;
+constexpr int kPassAt = 112;  // exponentials issued before the MUFU token is handed on (measured optimum)
 
 constexpr uint32_t kColS = 0;
 constexpr uint32_t kColP = 128;
 constexpr uint32_t kColO = 192;
-constexpr int kTmemCols = 256;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// 2^x for a pair on the FMA/ALU pipes: n = round(x) through the 1.5*2^23 magic constant, cubic minimax
-// of 2^f on [-0.5, 0.5], exponent inserted with one shift-add.  Inputs are clamped to >= -126.
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-  const float kMagic = 12582912.0f;
-  x.x = fmaxf(x.x, -126.0f);
-  x.y = fmaxf(x.y, -126.0f);
-  const float2 xf = __fadd2_rn(x, make_float2(kMagic, kMagic));
-  const float2 nf = __fadd2_rn(xf, make_float2(-kMagic, -kMagic));
-  const float2 f = __ffma2_rn(nf, make_float2(-1.0f, -1.0f), x);
-  float2 pl = __ffma2_rn(make_float2(0.0551716648f, 0.0551716648f), f, make_float2(0.2426111251f, 0.2426111251f));
-  pl = __ffma2_rn(pl, f, make_float2(0.6932609677f, 0.6932609677f));
-  pl = __ffma2_rn(pl, f, make_float2(0.9999280572f, 0.9999280572f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(xf.x) << 23));
-  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(xf.y) << 23));
-  return r;
-}
-
-// Timeline tracing (MHMR_ATTN_TRACE=file, kAb 7 / 8): SM-clock stamps of the protocol events of a few CTAs.
-__device__ uint32_t* g_attn_trace = nullptr;
-constexpr int kTraceIters = 40, kTraceEvents = 16, kTraceCtas = 8;
-__device__ __forceinline__ uint32_t clk_after(float dep) {
-  uint32_t t;
-  asm volatile("mov.u32 %0, %%clock;" : "=r"(t) : "f"(dep) : "memory");
-  return t;
-}
 
 // A condition the compilers cannot fold (always true).  ptxas schedules within basic blocks: a branch on it
 // keeps the instructions that follow from being woven into the instructions before it.
@@ -85,357 +70,24 @@ __device__ __forceinline__ bool opaque_true() {
   return v < 32u;
 }
 
-// kExpMode = how many of every eight score pairs take their exponential on the FMA pipes (cubic polynomial,
-// relative error 7.5e-5, far below the fp16 rounding of P) instead of MUFU.EX2: 0 (all MUFU) .. 3.
-template <int kExpMode, int kSK, int kSV, int kAb = 0>
-__global__ void __launch_bounds__(kAttnThreads, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
-                int T, int D, float scale_log2) {
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment (128B swizzle atoms) by POINTER arithmetic, so that the compiler keeps the
-  // shared address space (a round trip through uintptr_t degrades every access to generic LD/ST)
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + kTileBytes;               // [kSK]
-  uint8_t* sV = smem + kTileBytes * (1 + kSK);   // [kSV]
-  uint64_t* bars = reinterpret_cast<uint64_t*>((smem - smem_raw) >= kBarrierBytes ? smem_raw
-                                                                                  : smem + kTileBytes * (1 + kSK + kSV));
-  uint64_t* q_full = bars;                 // 1
-  uint64_t* k_full = bars + 1;             // [kSK]  TMA -> MMA
-  uint64_t* v_full = k_full + kSK;         // [kSV]  TMA -> MMA
-  uint64_t* k_empty = v_full + kSV;        // [kSK]  MMA -> TMA : Q K_j^T complete
-  uint64_t* v_empty = k_empty + kSK;       // [kSV]  MMA -> TMA : P_j V_j complete
-  uint64_t* s_full = v_empty + kSV;        // MMA -> softmax : S_j complete
-  uint64_t* s_empty = s_full + 1;          // softmax -> MMA : S_j now in registers
-  uint64_t* p_full = s_empty + 1;          // softmax -> MMA : P_j in TMEM (and O rescaled)
-  uint64_t* pv_done = p_full + 1;          // MMA -> softmax : O += P_j V_j complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
-  const int row0 = img * T;              // first token row of this image in the [B*T, 3D] matrix
-  const int q0 = q_tile * kBlockQ;
-  const int n_kv = (T + kBlockKV - 1) / kBlockKV;
-  // real keys of the last tile, rounded up to the 16-column granularity of the MMAs
-  const int last_valid = T - (n_kv - 1) * kBlockKV;
-  const int last_cols = (last_valid + 15) & ~15;
-
-  griddep_launch_dependents();
-  if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQKV);
-      mbar_init(q_full, 1);
-      for (int s = 0; s < kSK; ++s) {
-        mbar_init(&k_full[s], 1);
-        mbar_init(&k_empty[s], 1);
-      }
-      for (int s = 0; s < kSV; ++s) {
-        mbar_init(&v_full[s], 1);
-        mbar_init(&v_empty[s], 1);
-      }
-      mbar_init(s_full, 1);
-      mbar_init(s_empty, 4);
-      mbar_init(p_full, 4);
-      mbar_init(pv_done, 1);
-      fence_barrier_init();
-    }
-    __syncwarp();
-    tmem_alloc<kTmemCols>(tmem_slot);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  griddep_wait();  // qkv of the preceding GEMM is complete and visible
-  constexpr bool kTrace = (kAb == 7 || kAb == 8);
-  uint32_t* trace = nullptr;
-  if constexpr (kTrace) {
-    const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    // CTAs of the third wave onwards (steady state), every 37th
-    if (g_attn_trace != nullptr && lin >= 600 && (lin - 600) % 37 == 0 && (lin - 600) / 37 < kTraceCtas)
-      trace = g_attn_trace + ((lin - 600) / 37) * kTraceIters * kTraceEvents;
-    if (trace != nullptr && threadIdx.x == 64) {
-      uint32_t smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      trace[10] = smid;
-      trace[11] = clk_after(0.f);
-    }
-  }
-  auto stamp = [&](int j, int ev, float dep) {
-    if constexpr (kTrace) {
-      if (trace != nullptr && j < kTraceIters) trace[j * kTraceEvents + ev] = clk_after(dep);
-    }
-  };
-
-  if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    // (whole warp on uniform control flow; one elected lane issues -- see elect_one_sync)
-    if (elect_one_sync()) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_2d(sQ, &tmQKV, q_full, head * kHeadDim, row0 + q0);
-    }
-    // The K ring is released by Q K^T, the V ring by P V: the loads run up to kSK / kSV key tiles ahead,
-    // which hides the L2 -> smem latency (about one whole tile iteration) behind the softmax.
-    for (int j = 0; j < n_kv; ++j) {
-      const int sk = j % kSK, sv = j % kSV;
-      mbar_wait(&k_empty[sk], ((j / kSK) & 1u) ^ 1u);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&k_full[sk], kTileBytes);
-        tma_load_2d(sK + sk * kTileBytes, &tmQKV, &k_full[sk], D + head * kHeadDim, row0 + j * kBlockKV);
-      }
-      mbar_wait(&v_empty[sv], ((j / kSV) & 1u) ^ 1u);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&v_full[sv], kTileBytes);
-        tma_load_2d(sV + sv * kTileBytes, &tmQKV, &v_full[sv], 2 * D + head * kHeadDim, row0 + j * kBlockKV);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    // (whole warp on uniform control flow; one elected lane issues)
-    constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, false, true);  // B (V) is MN-major
-    const uint32_t t_s = tmem_base + kColS;
-    const uint32_t t_p = tmem_base + kColP;
-    const uint32_t t_o = tmem_base + kColO;
-    const uint64_t q_desc = make_sw128_desc(smem_u32(sQ), 16, 1024);
-
-    auto issue_qk = [&](int j) {
-      const int s = j % kSK;
-      const int ncols = (j == n_kv - 1) ? last_cols : kBlockKV;
-      const uint32_t idesc_qk = make_idesc_f16(128, ncols, false, false);
-      mbar_wait(&k_full[s], (j / kSK) & 1u);
-      tc_fence_after();
-      const uint64_t k_desc = make_sw128_desc(smem_u32(sK + s * kTileBytes), 16, 1024);
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int k = 0; k < kHeadDim / 16; ++k)
-          umma_f16_ss(t_s, q_desc + 2u * k, k_desc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
-        umma_commit(&k_empty[s]);
-        umma_commit(s_full);
-      }
-      __syncwarp();
-    };
-
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    for (int j = 0; j < n_kv; ++j) {
-      if (j + 1 < n_kv) {
-        mbar_wait(s_empty, j & 1u);  // softmax holds S_j in registers: S may be overwritten
-        tc_fence_after();
-        if constexpr (kTrace) { if (lane == 0) stamp(j, 6, 0.f); }
-        issue_qk(j + 1);
-        if constexpr (kTrace) { if (lane == 0) stamp(j, 7, 0.f); }
-      }
-      const int s = j % kSV;
-      mbar_wait(&v_full[s], (j / kSV) & 1u);
-      mbar_wait(p_full, j & 1u);
-      tc_fence_after();
-      if constexpr (kTrace) { if (lane == 0) stamp(j, 8, 0.f); }
-      // V tile: 128 keys (K) x 64 dims (N), N contiguous: MN-major, 8-key groups 1024 B apart.
-      const uint64_t v_desc = make_sw128_desc(smem_u32(sV + s * kTileBytes), 1024, 1024);
-      const int ksteps = ((j == n_kv - 1) ? last_cols : kBlockKV) / 16;
-      if (elect_one_sync()) {
-        for (int k = 0; k < ksteps; ++k) {
-          // A: 16 fp16 of P = 8 TMEM columns per K step; B: 16 keys = 2048 B per K step
-          umma_f16_ts(t_o, t_p + 8u * k, v_desc + 128u * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&v_empty[s]);
-        umma_commit(pv_done);
-      }
-      __syncwarp();
-      if constexpr (kTrace) { if (lane == 0) stamp(j, 9, 0.f); }
-    }
-  } else {
-    // ------------------------------ Softmax warps ------------------------------
-    const int sub = warp & 3;             // TMEM sub-partition (lane quarter) of this warp
-    const int row = sub * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(sub * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_base + kColS;
-    const uint32_t t_p = tmem_base + lane_base + kColP;
-    const uint32_t t_o = tmem_base + lane_base + kColO;
-    const bool warp_has_rows = (q0 + sub * 32) < T;  // warp-uniform
-
-    if (!warp_has_rows) {
-      // All 32 rows of this warp are beyond the sequence: their S/P/O lanes hold garbage that is never
-      // stored and never mixes with other rows (the MMAs are row-independent); keep the protocol alive.
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(s_full, j & 1u);
-        if (lane == 0) mbar_arrive(s_empty);
-        if (j > 0) mbar_wait(pv_done, (j - 1) & 1u);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-      }
-      mbar_wait(pv_done, (n_kv - 1) & 1u);
-    } else {
-      float m_used = -INFINITY;  // running max (log2 domain) actually used as the exponent offset
-      float l = 0.0f;
-
-      // One key tile of the online softmax with NCH (compile-time) 32-column chunks: 4 for full tiles, fewer
-      // for the ragged last tile.  Static chunk counts keep the 128 scores in registers (no local memory).
-      auto softmax_tile = [&](auto nch_c, auto last_c, int j) {
-        constexpr int NCH = decltype(nch_c)::value;
-        constexpr bool kLast = decltype(last_c)::value;  // static: the key mask costs 2 instructions per score
-        mbar_wait(s_full, j & 1u);
-        tc_fence_after();
-        if (warp == 2 && lane == 0) stamp(j, 0, 0.f);
-        uint32_t s[NCH][32];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
-        tmem_ld_wait();
-        if (warp == 2 && lane == 0) stamp(j, 1, __uint_as_float(s[0][0]));
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty);
-
-        if constexpr (kLast) {  // keys beyond T (or rows of the next image): -inf
-#pragma unroll
-          for (int c = 0; c < NCH; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= last_valid) s[c][i] = 0xff800000u;
-        }
-        // row max: independent chains (3-input max), then combine
-        float mx = -INFINITY;
-        if constexpr (kAb == 2 || kAb == 3 || kAb == 4 || kAb == 8) mx = fmaxf(__uint_as_float(s[0][0]), __uint_as_float(s[0][1]));
-#pragma unroll
-        for (int c = 0; c < ((kAb == 2 || kAb == 3 || kAb == 4 || kAb == 8) ? 0 : NCH); ++c) {
-          float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
-#pragma unroll
-          for (int i = 2; i < 32; i += 2)
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
-          mx = fmaxf(mx, m0);
-        }
-        if (warp == 2 && lane == 0) stamp(j, 2, mx);
-        const float m_new = fmaxf(m_used, mx * scale_log2);
-        const bool rescale = (m_new - m_used) > kRescaleThreshold;  // true on the first tile
-        float alpha = 1.0f;
-        if (rescale) {
-          alpha = exp2f(m_used - m_new);  // 0 on the first tile
-          m_used = m_new;
-        }
-        // exponentials (MUFU.EX2 is the binding pipe), packed f32x2 FMA/ADD, two accumulator pairs
-        const float2 sc2 = make_float2(scale_log2, scale_log2);
-        const float2 nm2 = make_float2(-m_used, -m_used);
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-        uint32_t p[NCH][16];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            if constexpr (kAb == 4 || kAb == 8) { p[c][i / 2] = s[c][i]; p[c][i / 2 + 1] = s[c][i + 2]; continue; }
-            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, nm2);
-            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3])), sc2, nm2);
-            const int pair = (i >> 1) & 7;  // pair index within a group of 8 pairs
-            const bool poly0 = (kExpMode >= 1 && pair == 0) || (kExpMode >= 2 && pair == 4);
-            const bool poly1 = (kExpMode >= 3) && (pair + 1 == 3);
-            const float2 e0 = (kAb == 1 || kAb == 3 || kAb == 4) ? t0 : poly0 ? ex2_poly2(t0) : make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
-            const float2 e1 = (kAb == 1 || kAb == 3 || kAb == 4) ? t1 : poly1 ? ex2_poly2(t1) : make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
-            acc0 = __fadd2_rn(acc0, e0);
-            acc1 = __fadd2_rn(acc1, e1);
-            const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
-            p[c][i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
-            p[c][i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-          }
-        }
-        l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
-        if (warp == 2 && lane == 0) stamp(j, 3, l);
-
-        if (j > 0) {
-          mbar_wait(pv_done, (j - 1) & 1u);  // P buffer free, O stable
-          tc_fence_after();
-          if (warp == 2 && lane == 0) stamp(j, 4, 0.f);
-          if (__any_sync(0xffffffffu, rescale)) {  // rare after the first tiles: small chunks
-#pragma unroll 1
-            for (int c = 0; c < kHeadDim / 8; ++c) {
-              uint32_t o[8];
-              tmem_ld_32x8(t_o + c * 8, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x8(t_o + c * 8, o);
-            }
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) tmem_st_32x16(t_p + c * 16, p[c]);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-        if (warp == 2 && lane == 0) stamp(j, 5, 0.f);
-      };
-
-      const int last_nch = (last_cols + 31) >> 5;  // 32-column chunks of the last tile that hold real keys
-      for (int j = 0; j < n_kv - 1; ++j) softmax_tile(std::integral_constant<int, 4>{}, std::false_type{}, j);
-      switch (last_nch) {
-        case 1: softmax_tile(std::integral_constant<int, 1>{}, std::true_type{}, n_kv - 1); break;
-        case 2: softmax_tile(std::integral_constant<int, 2>{}, std::true_type{}, n_kv - 1); break;
-        case 3: softmax_tile(std::integral_constant<int, 3>{}, std::true_type{}, n_kv - 1); break;
-        default: softmax_tile(std::integral_constant<int, 4>{}, std::true_type{}, n_kv - 1); break;
-      }
-
-      // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
-      mbar_wait(pv_done, (n_kv - 1) & 1u);
-      tc_fence_after();
-      const float inv_l = 1.0f / l;
-      const int q = q0 + row;
-      __half* dst = out + static_cast<int64_t>(row0 + q) * ldo + head * kHeadDim;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t o[32];
-        tmem_ld_32x32(t_o + c * 32, o);
-        tmem_ld_wait();
-        if (q < T) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 pk;
-            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const __half2 h = __floats2half2_rn(__uint_as_float(o[g * 8 + 2 * i]) * inv_l,
-                                                  __uint_as_float(o[g * 8 + 2 * i + 1]) * inv_l);
-              pw[i] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
-  }
+// Timeline tracing (MHMR_ATTN_ABLATE=7 MHMR_ATTN_TRACE=file): SM-clock stamps of the protocol events of a few CTAs.
+__device__ uint32_t* g_attn_trace = nullptr;
+constexpr int kTraceIters = 40, kTraceEvents = 16, kTraceCtas = 8;
+__device__ __forceinline__ uint32_t clk_after(float dep) {
+  uint32_t t;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(t) : "f"(dep) : "memory");
+  return t;
 }
 
+constexpr int kAttnThreads = 384;
+constexpr int kRegsIssue = 80, kRegsSoftmax = 208;  // 128 * (80 + 2 * 208) <= 64 K registers
+// Q tiles + K ring + V ring + 1 KB that covers both the 1024-byte alignment of the tiles and the barriers
+// (in front of the tiles when the alignment pad leaves room, behind them otherwise)
+constexpr int attn_smem_bytes(int sk, int sv) { return kTileBytes * (2 + sk + sv) + 1024; }
 
-
-// ---------------------------------------------------------------------------------------------------
-// Two query tiles per CTA (256 query rows), one CTA per SM, alternating exponent phases.
-//
-// Measured on the one-tile kernel above (SM-clock traces, tools/attn_trace.py): per key tile a softmax warp
-// spends ~1400 clk issuing its 128 MUFU.EX2 (+ the FFMA2/FADD2/F2FP woven in between) and ~900 clk on
-// everything else (TMEM load, row max, barrier round trips, P store).  The SM sub-partition's MUFU unit is
-// only kept busy when the two warps that share it (one per co-resident CTA) are in DIFFERENT phases -- and two
-// independent CTAs drift into the same phase and stay there (2250 vs 3450 clk per tile pair).  Here the two
-// query tiles live in ONE CTA, so the two warps of a sub-partition hand a token back and forth:
-// exps(tile 0, j) -> exps(tile 1, j) -> exps(tile 0, j+1) ...; each warp's other work runs under its
-// partner's exponentials.  K / V tiles are fetched once per 256 query rows.
-//
-//   CTA   = 384 threads = 3 warpgroups: warp 0 TMA, warp 1 MMA issuer (warps 2-3 idle) | warps 4-7 softmax
-//           of query tile 0 | warps 8-11 softmax of query tile 1 (setmaxnreg 80 / 208 / 208)
-//   TMEM  = 512 columns: per query tile  S (128 fp32) | P (64 cols = 128 fp16) | O (64 fp32)
-//   MMA order per key tile j:  S0(j+1) = Q0 K(j+1)^T | O1 += P1(j-1) V(j-1) | S1(j+1) | O0 += P0(j) V(j)
-constexpr int kAttn2Threads = 384;
-constexpr int kRegs2Issue = 80, kRegs2Softmax = 208;  // 128 * (80 + 2 * 208) <= 64 K registers
-constexpr int attn2_smem_bytes(int sk, int sv) { return kTileBytes * (2 + sk + sv) + 1024; }
-
-template <int kPass, int kSK, int kSV, int kAb = 0>
-__global__ void __launch_bounds__(kAttn2Threads, 1)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
+template <int kSK, int kSV, int kAb = 0>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
                  int T, int D, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -519,7 +171,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs2Issue));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, two ? 2 * kTileBytes : kTileBytes);
       tma_load_2d(sQ, &tmQKV, q_full, head * kHeadDim, row0 + q0);
@@ -540,7 +192,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs2Issue));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
     constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, false, true);  // B (V) is MN-major
     // S_t(j) = Q_t K_j^T; `release_k`: last reader of the K stage
     auto issue_qk = [&](int j, int t, bool release_k) {
@@ -609,10 +261,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
       issue_pv(n_kv - 1, 1, true);
     }
   } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs2Issue));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
   } else {
     // ------------------------------ Softmax warps ------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs2Softmax));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
     const int t = (warp - 4) >> 2;        // query tile of this warp
     const int sub = warp & 3;             // TMEM sub-partition (lane quarter) = SM sub-partition of this warp
     const int row = sub * 32 + lane;
@@ -739,9 +391,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
               asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(s[c][k])));
               s[c][k] = __float_as_uint(e);
             }
-            // hand the token on kPass exponentials into the run (full tiles; at the end of a short last tile):
-            // the partner needs ~350 clk from this arrive to its first MUFU
-            if ((NCH == 4 && c * 32 + k + 1 == kPass) || (NCH < 4 && c == NCH - 1 && k == 31)) {
+            // hand the token on kPassAt exponentials into the run (full tiles; at the end of a short last tile)
+            if ((NCH == 4 && c * 32 + k + 1 == kPassAt) || (NCH < 4 && c == NCH - 1 && k == 31)) {
               if (opaque_true()) pass_turn(j);
             }
           }
@@ -846,14 +497,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__
   }
 }
 
-int g_attn_exp_mode = -1;  // -1: not chosen yet (MHMR_ATTN_EXP, else kDefaultExpMode)
-constexpr int kDefaultExpMode = 0;
-int g_attn_stages = -1;    // 10 * K stages + V stages (MHMR_ATTN_STAGES, else kDefaultStages)
-constexpr int kDefaultStages = 244;
-int g_attn_ablate = -1;    // MHMR_ATTN_ABLATE: timing experiments only (wrong results), see tools/attn_ablate.py
+int g_attn_ablate = -1;  // MHMR_ATTN_ABLATE: timing / tracing experiments only (see the header)
 
 struct AttnArgs {
-  CUtensorMap tm;     // 128-row boxes (Q; K and V of the 128-key kernel)
+  CUtensorMap tm;
   __half* out;
   int64_t ldo;
   int T, D;
@@ -862,19 +509,13 @@ struct AttnArgs {
   cudaStream_t stream;
 };
 
-template <int kExpMode, int kSK, int kSV, int kAb>
+template <int kAb>
 int attn_launch(const AttnArgs& a) {
-  constexpr int smem = attn_smem_bytes(kSK, kSV);
-  auto kern = attn_fwd_kernel<kExpMode, kSK, kSV, kAb>;
+  constexpr int smem = attn_smem_bytes(kStagesK, kStagesV);
+  auto kern = attn_fwd_kernel<kStagesK, kStagesV, kAb>;
   static bool attr_set = false;
   if (!attr_set) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (std::getenv("MHMR_ATTN_VERBOSE") != nullptr) {
-      int ctas = 0;
-      cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, kAttnThreads, smem);
-      fprintf(stderr, "[mhmr] attention<%d,%d,%d,%d>: %d B dynamic smem, occupancy query -> %d CTAs/SM (%s)\n", kExpMode,
-              kSK, kSV, kAb, smem, ctas, cudaGetErrorString(oe));
-    }
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -892,69 +533,7 @@ int attn_launch(const AttnArgs& a) {
   return MHMR_OK;
 }
 
-template <int kPass, int kSK, int kSV, int kAb>
-int attn2_launch(const AttnArgs& a) {
-  constexpr int smem = attn2_smem_bytes(kSK, kSV);
-  auto kern = attn_fwd2_kernel<kPass, kSK, kSV, kAb>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((a.grid.x + 1) / 2, a.grid.y, a.grid.z);
-  cfg.blockDim = dim3(kAttn2Threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = a.stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.tm, a.out, a.ldo, a.T, a.D, a.scale_log2));
-  MHMR_CUDA_CHECK(cudaGetLastError());
-  return MHMR_OK;
-}
-
-int g_attn_pass = -1;  // MHMR_ATTN_PASS: exponentials issued before the MUFU token is handed on
-
-template <int kSK, int kSV>
-int attn2_dispatch(const AttnArgs& a, int /*exp_mode*/, int ablate) {
-  if (g_attn_pass < 0) {
-    const char* e = std::getenv("MHMR_ATTN_PASS");
-    g_attn_pass = (e != nullptr) ? atoi(e) : 112;
-  }
-  if (ablate == 7) return attn2_launch<64, kSK, kSV, 7>(a);
-  if (ablate == 1) return attn2_launch<64, kSK, kSV, 1>(a);
-  if (ablate == 4) return attn2_launch<64, kSK, kSV, 4>(a);
-  switch (g_attn_pass) {
-    case 32: return attn2_launch<32, kSK, kSV, 0>(a);
-    case 48: return attn2_launch<48, kSK, kSV, 0>(a);
-    case 80: return attn2_launch<80, kSK, kSV, 0>(a);
-    case 96: return attn2_launch<96, kSK, kSV, 0>(a);
-    case 64: return attn2_launch<64, kSK, kSV, 0>(a);
-    case 128: return attn2_launch<128, kSK, kSV, 0>(a);
-    default: return attn2_launch<112, kSK, kSV, 0>(a);
-  }
-}
-
-template <int kSK, int kSV>
-int attn_dispatch(const AttnArgs& a, int exp_mode, int ablate) {
-  if (ablate == 7) return attn_launch<0, kSK, kSV, 7>(a);
-  if (ablate == 8) return attn_launch<0, kSK, kSV, 8>(a);
-  if (ablate == 1) return attn_launch<0, kSK, kSV, 1>(a);
-  if (ablate == 4) return attn_launch<0, kSK, kSV, 4>(a);
-  switch (exp_mode) {
-    case 1: return attn_launch<1, kSK, kSV, 0>(a);
-    case 2: return attn_launch<2, kSK, kSV, 0>(a);
-    case 3: return attn_launch<3, kSK, kSV, 0>(a);
-    default: return attn_launch<0, kSK, kSV, 0>(a);
-  }
-}
-
 }  // namespace
-
-void attention_set_exp_mode(int mode) { g_attn_exp_mode = mode; }
 
 // qkv: [B*T, 3*D] fp16 (row pitch ld_qkv), q|k|v column blocks, head h = columns h*64..h*64+63 of each.
 // out: [B*T, D] fp16 (row pitch ldo).
@@ -967,13 +546,7 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   int rc = make_tmap_2d(&a.tm, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<uint64_t>(B) * T,
                         3ull * D, ld_qkv * 2, 128, 64, true);
   if (rc != MHMR_OK) return rc;
-  if (g_attn_exp_mode < 0) {
-    const char* e = std::getenv("MHMR_ATTN_EXP");
-    g_attn_exp_mode = (e != nullptr && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : kDefaultExpMode;
-  }
-  if (g_attn_stages < 0) {
-    const char* e = std::getenv("MHMR_ATTN_STAGES");
-    g_attn_stages = (e != nullptr) ? atoi(e) : kDefaultStages;
+  if (g_attn_ablate < 0) {
     const char* ab = std::getenv("MHMR_ATTN_ABLATE");
     g_attn_ablate = (ab != nullptr) ? atoi(ab) : 0;
   }
@@ -982,17 +555,18 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   a.T = T;
   a.D = D;
   a.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-  a.grid = dim3((T + kBlockQ - 1) / kBlockQ, D / kHeadDim, B);
+  a.grid = dim3((T + 2 * kBlockQ - 1) / (2 * kBlockQ), D / kHeadDim, B);
   a.stream = stream;
+  if (g_attn_ablate == 1) return attn_launch<1>(a);
+  if (g_attn_ablate == 4) return attn_launch<4>(a);
   const char* trace_path = std::getenv("MHMR_ATTN_TRACE");
-  uint32_t* d_trace = nullptr;
-  const size_t trace_words = static_cast<size_t>(kTraceCtas) * kTraceIters * kTraceEvents;
-  if (trace_path != nullptr && (g_attn_ablate == 7 || g_attn_ablate == 8)) {
+  if (g_attn_ablate == 7 && trace_path != nullptr) {
+    uint32_t* d_trace = nullptr;
+    const size_t trace_words = static_cast<size_t>(kTraceCtas) * kTraceIters * kTraceEvents;
     MHMR_CUDA_CHECK(cudaMalloc(&d_trace, trace_words * 4));
     MHMR_CUDA_CHECK(cudaMemset(d_trace, 0, trace_words * 4));
     MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &d_trace, sizeof(d_trace)));
-    rc = (g_attn_stages == 244) ? attn2_dispatch<4, 4>(a, g_attn_exp_mode, g_attn_ablate)
-                                : attn_dispatch<3, 3>(a, g_attn_exp_mode, g_attn_ablate);
+    rc = attn_launch<7>(a);
     if (rc != MHMR_OK) return rc;
     MHMR_CUDA_CHECK(cudaStreamSynchronize(stream));
     std::vector<uint32_t> h(trace_words);
@@ -1006,16 +580,7 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
     MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &d_trace, sizeof(d_trace)));
     return MHMR_OK;
   }
-  switch (g_attn_stages) {
-    case 233: return attn2_dispatch<3, 3>(a, g_attn_exp_mode, g_attn_ablate);
-    case 244: return attn2_dispatch<4, 4>(a, g_attn_exp_mode, g_attn_ablate);
-    case 22: return attn_dispatch<2, 2>(a, g_attn_exp_mode, g_attn_ablate);
-    case 32: return attn_dispatch<3, 2>(a, g_attn_exp_mode, g_attn_ablate);
-    case 23: return attn_dispatch<2, 3>(a, g_attn_exp_mode, g_attn_ablate);
-    case 33: return attn_dispatch<3, 3>(a, g_attn_exp_mode, g_attn_ablate);
-    default: MHMR_REQUIRE(false, "MHMR_ATTN_STAGES must be 22, 32, 23 or 33");
-  }
-  return MHMR_OK;
+  return attn_launch<0>(a);
 }
 
 }  // namespace mhmr

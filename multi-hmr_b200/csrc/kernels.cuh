@@ -8,9 +8,6 @@ namespace mhmr {
 int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ldo, int B, int T, int D,
                       cudaStream_t stream);
 
-// 0: all exponentials on MUFU.EX2; 1: 3 of 8 on the FMA pipes (cubic polynomial)
-void attention_set_exp_mode(int mode);
-
 // ---- vit_misc.cu -----------------------------------------------------------------------------
 int im2col_patch14(const float* x, __half* A, int B, int S, int ldA, cudaStream_t stream);
 int cls_rows(float* X, const float* cls_pos, int B, int T, int D, cudaStream_t stream);

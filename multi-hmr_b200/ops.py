@@ -36,11 +36,6 @@ def gemm_f16(a, w, epilogue, out, bias=None, gamma=None, rowadd=None, rows_in=0,
     return out
 
 
-def set_attention_exp_mode(mode: int):
-    """0: every softmax exponential on MUFU.EX2; 1: three of eight on the FMA pipes (cubic polynomial)."""
-    check(_lib.load().mhmr_set_attention_exp_mode(c_int(mode)), "mhmr_set_attention_exp_mode")
-
-
 def attention(qkv, B, T, D, out=None):
     """qkv [B*T, 3*D] fp16 -> out [B*T, D] fp16, heads of 64 dims, softmax(q k^T / 8) v per image."""
     _cuda(qkv)

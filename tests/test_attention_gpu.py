@@ -24,18 +24,16 @@ def _ref(qkv, B, T, D):
     (1, 256 + 40, 64, 1.0), # tail of 40 keys: 48 columns, two chunks
     (1, 384 + 100, 64, 1.0),# tail of 100 keys: 112 columns, four chunks
     (1, 33, 64, 1.0),       # one short tile, query warps 2..3 have no rows
+    (1, 130, 64, 1.0),      # second query tile with 2 rows: three of its warps only keep the protocol alive
+    (3, 600, 128, 1.0),     # odd number of query tiles: the last CTA of an image holds a single tile
+    (1, 2 * 128 + 1, 64, 8.0),  # peaky softmax across three key tiles + single-row last query tile
 ])
-@pytest.mark.parametrize("exp_mode", [0, 1, 3])
-def test_attention_matches_fp32(cuda_device, B, T, D, scale, exp_mode):
+def test_attention_matches_fp32(cuda_device, B, T, D, scale):
     from multihmr_b200 import ops
 
     g = torch.Generator(device="cpu").manual_seed(B * 1000 + T + D)
     qkv = (torch.randn(B * T, 3 * D, generator=g) * scale).to(cuda_device).half()
-    ops.set_attention_exp_mode(exp_mode)
-    try:
-        out = ops.attention(qkv, B, T, D)
-    finally:
-        ops.set_attention_exp_mode(0)
+    out = ops.attention(qkv, B, T, D)
     ref = _ref(qkv, B, T, D)
     err = (out.float() - ref).abs().max().item()
     # P is rounded to fp16 (2^-11 relative) before the PV product and the output is fp16

@@ -1,4 +1,5 @@
-"""Times mhmr_op_attention (ViT-L @896, batch 8) under MHMR_ATTN_* environment switches (one process each)."""
+"""Times mhmr_op_attention (ViT-L @896, batch 8): the product kernel, without its exponentials
+(MHMR_ATTN_ABLATE=1) and with the barrier / TMEM protocol only (=4); one process each."""
 import json
 import os
 import subprocess
@@ -21,8 +22,7 @@ print(json.dumps(dict(ms=round(ms, 4), tflops=round(4.0 * B * T * T * D / ms / 1
 ''' % (ROOT, ROOT)
 
 res = []
-envs = [dict(MHMR_ATTN_STAGES="33")]
-envs += [dict(MHMR_ATTN_STAGES="244", MHMR_ATTN_PASS=str(m)) for m in (96, 112, 128)]
+envs = [dict(), dict(MHMR_ATTN_ABLATE="1"), dict(MHMR_ATTN_ABLATE="4")]
 for env in envs:
     e = dict(os.environ, MHMR_ATTN_VERBOSE="1")
     e.update(env)

@@ -64,14 +64,11 @@ def bench_attention(dev, flush):
         out = torch.empty(B * T, D, device=dev, dtype=torch.float16)
         q, k, v = qkv.view(B, T, 3, D // 64, 64).permute(2, 0, 3, 1, 4)
         ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B * T, D) if B * T < 20000 else None
-        for mode in (0, 1, 2, 3):
-            ops.set_attention_exp_mode(mode)
-            ms = timeit(lambda: ops.attention(qkv, B, T, D, out=out), flush=flush)
-            err = (out.float() - ref).abs().max().item() if ref is not None else None
-            res.append(dict(op="attention", B=B, T=T, D=D, exp_mode=mode, ms=round(ms, 4),
-                            tflops=round(4.0 * B * T * T * D / ms / 1e9, 1), max_err=err))
-            print(res[-1], flush=True)
-        ops.set_attention_exp_mode(0)
+        ms = timeit(lambda: ops.attention(qkv, B, T, D, out=out), flush=flush)
+        err = (out.float() - ref).abs().max().item() if ref is not None else None
+        res.append(dict(op="attention", B=B, T=T, D=D, ms=round(ms, 4),
+                        tflops=round(4.0 * B * T * T * D / ms / 1e9, 1), max_err=err))
+        print(res[-1], flush=True)
     return res
 
 

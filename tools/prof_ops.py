@@ -14,8 +14,6 @@ M = B * T
 if what == "attention":
     qkv = torch.randn(M, 3 * D, device=dev).half()
     out = torch.empty(M, D, device=dev, dtype=torch.float16)
-    if len(sys.argv) > 2:
-        ops.set_attention_exp_mode(int(sys.argv[2]))
     for _ in range(3):
         ops.attention(qkv, B, T, D, out=out)
 else:
