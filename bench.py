@@ -287,9 +287,14 @@ def run_ours(args):
     vit_tflops = vit_flops_per_image(w["backbone"], S) * B * args.steps / max(vit_ms, 1e-9) / 1e9
     roofline = None
     if dom:
+        traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(dom, {}).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": dom, "achieved": round(fam[dom]["tflops"], 1),
                     "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": round(fam[dom]["tflops"] / peaks["tflops"], 4),
-                    "traffic": None, "peak_source": peaks["source"] + ", sustained cuBLAS bf16",
+                    "traffic": traffic, "peak_source": peaks["source"] + ", sustained cuBLAS bf16",
                     "families": {k: {a: round(b, 4) for a, b in v.items()} for k, v in fam.items()},
                     "vit_backbone": {"tflops": round(vit_tflops, 1), "frac": round(vit_tflops / peaks["tflops"], 4),
                                      "ms_per_step": round(vit_ms / args.steps, 3)},
