@@ -58,6 +58,11 @@ int mhmr_op_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int
 int mhmr_op_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int B, int T, int D,
                       void* stream);
 
+/* Image preprocessing on the device: uint8 [B,H,W,3] (RGB, HWC) -> fp32 [B,3,H,W] through a [3][256] fp32 table.
+ * Replaces reference utils/image.py:12-24 `normalize_rgb` (called from demo.py:48 `open_image`); with the table the
+ * host derives from that function the output is bit-identical, and the upload is 4x smaller.  W % 4 == 0. */
+int mhmr_op_normalize_u8(const void* img_u8, const float* lut, float* out, int B, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Engine: the whole `Model.forward(x, K)` path (reference model.py:205-349) behind one handle
  * ---------------------------------------------------------------------------------------------- */

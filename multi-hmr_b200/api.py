@@ -29,14 +29,39 @@ def normalize_rgb(img: np.ndarray, imagenet_normalization: bool = True) -> np.nd
     return img.astype(np.float32)
 
 
+def normalize_rgb_table() -> np.ndarray:
+    """[3, 256] fp32: `normalize_rgb` of every uint8 value in every channel (the table of the device kernel)."""
+    ramp = np.repeat(np.arange(256, dtype=np.uint8)[None, :, None], 3, axis=2)
+    return np.ascontiguousarray(normalize_rgb(ramp)[:, 0, :])
+
+
+_LUT_CACHE = {}
+
+
+def normalize_rgb_device(img_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 [B,H,W,3] on a CUDA device -> normalised fp32 [B,3,H,W], bit-identical to `normalize_rgb` on the
+    host (hand-written kernel, `mhmr_op_normalize_u8`); 4x less to upload than the fp32 image."""
+    from . import ops
+
+    key = (img_u8.device.type, img_u8.device.index)
+    if key not in _LUT_CACHE:
+        _LUT_CACHE[key] = torch.from_numpy(normalize_rgb_table()).to(img_u8.device)
+    return ops.normalize_u8(img_u8.contiguous(), _LUT_CACHE[key])
+
+
 def open_image(img_path, img_size, device=torch.device("cuda")):
-    """Open, resize keeping the aspect ratio, zero-pad to a square, normalise (demo.py:27-51)."""
+    """Open, resize keeping the aspect ratio, zero-pad to a square, normalise (demo.py:27-51).  On a CUDA
+    device the padded uint8 image is uploaded and normalised there (same values, a quarter of the bytes)."""
     from PIL import Image, ImageOps
 
     img_pil = Image.open(img_path).convert("RGB")
     img_pil_full = img_pil.copy()
     img_pil = ImageOps.contain(img_pil, (img_size, img_size))
     img_pil = ImageOps.pad(img_pil, size=(img_size, img_size))
+    device = torch.device(device)
+    if device.type == "cuda" and img_size % 4 == 0:
+        u8 = torch.from_numpy(np.ascontiguousarray(np.asarray(img_pil))).unsqueeze(0).to(device)
+        return normalize_rgb_device(u8), img_pil_full
     x = torch.from_numpy(normalize_rgb(np.asarray(img_pil))).unsqueeze(0).to(device)
     return x, img_pil_full
 

@@ -35,4 +35,9 @@ int mhmr_op_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, i
                            D, static_cast<cudaStream_t>(stream));
 }
 
+int mhmr_op_normalize_u8(const void* img_u8, const float* lut, float* out, int B, int H, int W, void* stream) {
+  MHMR_REQUIRE(img_u8 != nullptr && lut != nullptr && out != nullptr, "null argument");
+  return normalize_u8(static_cast<const uint8_t*>(img_u8), lut, out, B, H, W, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

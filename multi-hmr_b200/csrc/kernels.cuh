@@ -10,6 +10,7 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
 
 // ---- vit_misc.cu -----------------------------------------------------------------------------
 int im2col_patch14(const float* x, __half* A, int B, int S, int ldA, cudaStream_t stream);
+int normalize_u8(const uint8_t* img, const float* lut, float* out, int B, int H, int W, cudaStream_t stream);
 int cls_rows(float* X, const float* cls_pos, int B, int T, int D, cudaStream_t stream);
 int layernorm(const float* X, const float* gamma, const float* beta, __half* out16, int64_t ld16,
               float* out32, int64_t ld32, int M, int D, float eps, int rows_in, int skip,

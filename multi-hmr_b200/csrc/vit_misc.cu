@@ -1,5 +1,7 @@
 // Memory-bound helpers of the ViT backbone: patch gathering (im2col for the 14x14/14 conv), LayerNorm
 // with fp16 / fp32 outputs, cls-token row initialisation, fp32->fp16 weight repacking.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace mhmr {
@@ -22,6 +24,37 @@ __global__ void im2col_patch14_kernel(const float* __restrict__ x, __half* __res
     const int c = k / 196, r = k - c * 196;
     const int py = r / 14, px = r - py * 14;
     dst[k] = __float2half_rn(src[(static_cast<int64_t>(c) * S + gy * 14 + py) * S + gx * 14 + px]);
+  }
+}
+
+// uint8 HWC image -> normalised fp32 CHW through a [3][256] table (reference utils/image.py:12-24 `normalize_rgb`:
+// ((v / 255) - mean_c) / std_c evaluated in float64 and rounded to fp32 -- the host builds the table with exactly
+// those numpy operations, so the device output is bit-identical to the reference's host preprocessing).
+// One thread per 4 pixels of a row: 12 contiguous bytes in, three coalesced float4 out.
+__global__ void normalize_u8_kernel(const uint8_t* __restrict__ img, const float* __restrict__ lut,
+                                    float* __restrict__ out, int H, int W, int64_t n_quads) {
+  __shared__ float s_lut[3 * 256];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const int wq = W / 4;
+  for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < n_quads;
+       q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int xq = static_cast<int>(q % wq);
+    const int64_t row = q / wq;              // b * H + y
+    const int64_t b = row / H;
+    const int y = static_cast<int>(row - b * H);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(img + (row * W + xq * 4) * 3);
+    const uint32_t w0 = src[0], w1 = src[1], w2 = src[2];  // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+    float4 r, g, bl;
+    r.x = s_lut[w0 & 255u];               g.x = s_lut[256 + ((w0 >> 8) & 255u)];   bl.x = s_lut[512 + ((w0 >> 16) & 255u)];
+    r.y = s_lut[w0 >> 24];                g.y = s_lut[256 + (w1 & 255u)];          bl.y = s_lut[512 + ((w1 >> 8) & 255u)];
+    r.z = s_lut[(w1 >> 16) & 255u];       g.z = s_lut[256 + (w1 >> 24)];           bl.z = s_lut[512 + (w2 & 255u)];
+    r.w = s_lut[(w2 >> 8) & 255u];        g.w = s_lut[256 + ((w2 >> 16) & 255u)];  bl.w = s_lut[512 + (w2 >> 24)];
+    float* o = out + ((b * 3) * H + y) * static_cast<int64_t>(W) + xq * 4;
+    const int64_t plane = static_cast<int64_t>(H) * W;
+    *reinterpret_cast<float4*>(o) = r;
+    *reinterpret_cast<float4*>(o + plane) = g;
+    *reinterpret_cast<float4*>(o + 2 * plane) = bl;
   }
 }
 
@@ -103,6 +136,17 @@ int im2col_patch14(const float* x, __half* A, int B, int S, int ldA, cudaStream_
   MHMR_REQUIRE(S % 14 == 0 && ldA >= 588, "im2col: bad geometry");
   const int N = (S / 14) * (S / 14);
   im2col_patch14_kernel<<<B * N, 128, 0, stream>>>(x, A, B, S, ldA);
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+int normalize_u8(const uint8_t* img, const float* lut, float* out, int B, int H, int W, cudaStream_t stream) {
+  MHMR_REQUIRE(B > 0 && H > 0 && W > 0 && W % 4 == 0, "normalize_u8: width must be a multiple of 4");
+  MHMR_REQUIRE((reinterpret_cast<uintptr_t>(img) & 3u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
+               "normalize_u8: image must be 4-byte aligned, output 16-byte aligned");
+  const int64_t n_quads = static_cast<int64_t>(B) * H * (W / 4);
+  const int blocks = static_cast<int>(std::min<int64_t>((n_quads + 255) / 256, 148 * 8));
+  normalize_u8_kernel<<<blocks, 256, 0, stream>>>(img, lut, out, H, W, n_quads);
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }

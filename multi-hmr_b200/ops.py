@@ -36,6 +36,18 @@ def gemm_f16(a, w, epilogue, out, bias=None, gamma=None, rowadd=None, rows_in=0,
     return out
 
 
+def normalize_u8(img_u8, lut):
+    """uint8 [B,H,W,3] -> fp32 [B,3,H,W]: out[b,c,y,x] = lut[c, img[b,y,x,c]] (device-side `normalize_rgb`)."""
+    _cuda(img_u8, lut)
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[-1] == 3 and img_u8.is_contiguous()
+    assert lut.dtype == torch.float32 and tuple(lut.shape) == (3, 256) and lut.is_contiguous()
+    B, H, W, _ = img_u8.shape
+    out = torch.empty(B, 3, H, W, device=img_u8.device, dtype=torch.float32)
+    rc = _lib.load().mhmr_op_normalize_u8(ptr(img_u8), ptr(lut), ptr(out), c_int(B), c_int(H), c_int(W), stream_ptr())
+    check(rc, "mhmr_op_normalize_u8")
+    return out
+
+
 def attention(qkv, B, T, D, out=None):
     """qkv [B*T, 3*D] fp16 -> out [B*T, D] fp16, heads of 64 dims, softmax(q k^T / 8) v per image."""
     _cuda(qkv)

@@ -141,12 +141,36 @@ def run_case(name, case, out_dir):
     print(f"{name}: reference == oracle (max abs err {worst:.2e}), persons={n_p}, keys={len(keys)}")
 
 
+def run_normalize_rgb(out_dir):
+    """Golden of the preprocessing step: the reference's own `normalize_rgb`
+    (utils/image.py:12-24) applied to every uint8 value in every channel -> a [3, 256] fp32 table, plus its output
+    on a seeded random image.  The host restatement (multihmr_b200.api.normalize_rgb) and the device kernel must
+    reproduce it bit for bit."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_ref_utils_image", os.path.join(REFERENCE, "utils", "image.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ramp = np.repeat(np.arange(256, dtype=np.uint8)[None, :, None], 3, axis=2)       # [1, 256, 3]
+    table = mod.normalize_rgb(ramp)[:, 0, :]                                          # [3, 256]
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, size=(37, 53, 3), dtype=np.uint8)
+    out = mod.normalize_rgb(img)
+    from multihmr_b200 import api
+
+    assert np.array_equal(api.normalize_rgb(img), out), "host restatement of normalize_rgb differs from the reference"
+    np.savez_compressed(os.path.join(out_dir, "normalize_rgb.npz"), table=table, image=img, normalized=out)
+    print(f"normalize_rgb: table {table.shape} {table.dtype}, restatement bit-exact")
+
+
 def main():
     assert os.path.isdir(REFERENCE), "make_golden needs the reference checkout (build container only)"
     install_shims()
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     only = sys.argv[1:]
+    if not only or "normalize_rgb" in only:
+        run_normalize_rgb(out_dir)
     for name, case in CASES.items():
         if only and name not in only:
             continue
