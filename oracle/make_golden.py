@@ -159,7 +159,8 @@ def run_normalize_rgb(out_dir):
     from multihmr_b200 import api
 
     assert np.array_equal(api.normalize_rgb(img), out), "host restatement of normalize_rgb differs from the reference"
-    np.savez_compressed(os.path.join(out_dir, "normalize_rgb.npz"), table=table, image=img, normalized=out)
+    np.savez_compressed(os.path.join(out_dir, "normalize_rgb.npz"), table=np.ascontiguousarray(table), image=img,
+                        normalized=np.ascontiguousarray(out))
     print(f"normalize_rgb: table {table.shape} {table.dtype}, restatement bit-exact")
 
 

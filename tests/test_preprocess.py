@@ -47,7 +47,7 @@ def test_device_normalize_matches_reference_bit_for_bit(cuda_device):
     from multihmr_b200 import api, ops
 
     g = _golden()
-    lut = torch.from_numpy(g["table"]).to(cuda_device)
+    lut = torch.from_numpy(np.ascontiguousarray(g["table"])).to(cuda_device)  # (npz keeps the Fortran order)
     gen = torch.Generator().manual_seed(11)
     img = torch.randint(0, 256, (3, 56, 64, 3), generator=gen, dtype=torch.uint8)
     img[0, 0, :, 0] = torch.arange(64, dtype=torch.uint8) * 4          # every region of the table
