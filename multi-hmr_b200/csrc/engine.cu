@@ -1,7 +1,6 @@
 // Engine: weights, workspaces, TMA plans and the launch sequence of the whole Multi-HMR forward
 // (reference model.py:205-349) behind the C-ABI of include/mhmr.h.
 #include <cmath>
-#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -33,7 +32,6 @@ constexpr int kCamDim = 99;
 struct VitLayer {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bproj, *ls1, *bfc1, *bfc2, *ls2;
   __half *Wqkv, *Wproj, *Wfc1, *Wfc2;
-  float *cs_qkv = nullptr, *bqkv_f = nullptr, *cs_fc1 = nullptr, *bfc1_f = nullptr;  // fused-LN by-products
   GemmPlan qkv, proj, fc1, fc2;
 };
 struct HphLayer {
@@ -48,10 +46,6 @@ struct mhmr_engine {
   mhmr_config cfg{};
   int D = 0, depth = 0, heads = 0, res = 0, N = 0, T = 0, C = 0, Cp = 0, Cq = 0, nkv = 0, ndec = 0;
   bool finalized = false;
-  bool fuse_ln = false;  // LayerNorm folded into the neighbouring GEMM epilogues (MHMR_FUSE_LN=1 enables; measured slower and less accurate at full size than the separate LN kernel)
-  __half* X16 = nullptr;            // fp16 copy of the residual stream (A operand of qkv / fc1 when fused)
-  float *statsA = nullptr, *statsB = nullptr;  // [max_batch*T, stat_slots, 2] partial row (sum, sum of squares)
-  int stat_slots = 0;
   std::map<std::string, DevBuf> weights;   // raw fp32 device copies, keyed like the state_dict
   std::map<std::string, DevBuf> tables;    // int32 tables
   std::vector<void*> owned;                // everything cudaMalloc'ed (freed in destroy)
@@ -178,16 +172,8 @@ int finalize_vit(mhmr_engine* e, cudaStream_t st) {
   TRY(e->alloc(&e->O16, M * D));
   TRY(e->alloc(&e->H16, M * 4 * D));
 
-  if (e->fuse_ln) {
-    TRY(e->alloc(&e->X16, M * D));
-    e->stat_slots = gemm_stat_slots(D, pick_bn(D));
-    TRY(e->alloc(&e->statsA, M * e->stat_slots * 2));
-    TRY(e->alloc(&e->statsB, M * e->stat_slots * 2));
-  }
-  const float inv_dim = 1.0f / static_cast<float>(D);
   GemmEpi ep;
   ep.rowadd = e->rowadd; ep.out = e->X; ep.ldo = D; ep.rows_in = N; ep.rows_out = T; ep.row_off = 1;
-  if (e->fuse_ln) { ep.out16 = e->X16; ep.ld16 = D; ep.stats_out = e->statsB; ep.stat_slots = e->stat_slots; }
   TRY(gemm_plan_init(&e->patch_plan, e->A16, 592, e->Wpatch, 592, Bm * N, D, 588, EPI_ROWADD_F32, ep, pick_bn(D)));
 
   e->vit.resize(e->depth);
@@ -203,37 +189,17 @@ int finalize_vit(mhmr_engine* e, cudaStream_t st) {
     NEEDW(wfc2, b + "mlp.fc2.weight", 4ll * D * D) NEEDW(bfc2, b + "mlp.fc2.bias", D)
     L.ln1_g = n1g; L.ln1_b = n1b; L.ln2_g = n2g; L.ln2_b = n2b;
     L.bqkv = bqkv; L.bproj = bproj; L.ls1 = ls1; L.bfc1 = bfc1; L.bfc2 = bfc2; L.ls2 = ls2;
+    TRY(to_f16(e, wqkv, D, 3 * D, D, D, &L.Wqkv, st));
     TRY(to_f16(e, wproj, D, D, D, D, &L.Wproj, st));
+    TRY(to_f16(e, wfc1, D, 4 * D, D, D, &L.Wfc1, st));
     TRY(to_f16(e, wfc2, 4 * D, D, 4 * D, 4 * D, &L.Wfc2, st));
     GemmEpi a; a.bias = bqkv; a.out = e->QKV16; a.ldo = 3 * D;
-    GemmEpi f1; f1.bias = bfc1; f1.out = e->H16; f1.ldo = 4 * D;
+    TRY(gemm_plan_init(&L.qkv, e->Xn16, D, L.Wqkv, D, static_cast<int>(M), 3 * D, D, EPI_BIAS_F16, a, pick_bn(3 * D)));
     GemmEpi p; p.bias = bproj; p.gamma = ls1; p.out = e->X; p.ldo = D;
-    GemmEpi f2; f2.bias = bfc2; f2.gamma = ls2; f2.out = e->X; f2.ldo = D;
-    const __half* a_in = e->Xn16;
-    if (e->fuse_ln) {
-      // LN1 folded into qkv, LN2 into fc1: W' = gamma (.) W in fp16, column sums, bias' = b + W beta
-      TRY(e->alloc(&L.Wqkv, static_cast<size_t>(3) * D * D));
-      TRY(e->alloc(&L.cs_qkv, 3 * D));
-      TRY(e->alloc(&L.bqkv_f, 3 * D));
-      TRY(fold_ln(wqkv, n1g, n1b, bqkv, 3 * D, D, L.Wqkv, D, L.cs_qkv, L.bqkv_f, st));
-      TRY(e->alloc(&L.Wfc1, static_cast<size_t>(4) * D * D));
-      TRY(e->alloc(&L.cs_fc1, 4 * D));
-      TRY(e->alloc(&L.bfc1_f, 4 * D));
-      TRY(fold_ln(wfc1, n2g, n2b, bfc1, 4 * D, D, L.Wfc1, D, L.cs_fc1, L.bfc1_f, st));
-      a.bias = L.bqkv_f; a.colsum = L.cs_qkv; a.ln_stats = e->statsB; a.ln_slots = e->stat_slots;
-      a.ln_inv_dim = inv_dim; a.ln_eps = 1e-6f;
-      f1.bias = L.bfc1_f; f1.colsum = L.cs_fc1; f1.ln_stats = e->statsA; f1.ln_slots = e->stat_slots;
-      f1.ln_inv_dim = inv_dim; f1.ln_eps = 1e-6f;
-      p.out16 = e->X16; p.ld16 = D; p.stats_out = e->statsA; p.stat_slots = e->stat_slots;
-      f2.out16 = e->X16; f2.ld16 = D; f2.stats_out = e->statsB; f2.stat_slots = e->stat_slots;
-      a_in = e->X16;
-    } else {
-      TRY(to_f16(e, wqkv, D, 3 * D, D, D, &L.Wqkv, st));
-      TRY(to_f16(e, wfc1, D, 4 * D, D, D, &L.Wfc1, st));
-    }
-    TRY(gemm_plan_init(&L.qkv, a_in, D, L.Wqkv, D, static_cast<int>(M), 3 * D, D, EPI_BIAS_F16, a, pick_bn(3 * D)));
     TRY(gemm_plan_init(&L.proj, e->O16, D, L.Wproj, D, static_cast<int>(M), D, D, EPI_LS_RESID_F32, p, pick_bn(D)));
-    TRY(gemm_plan_init(&L.fc1, a_in, D, L.Wfc1, D, static_cast<int>(M), 4 * D, D, EPI_BIAS_GELU_F16, f1, pick_bn(4 * D)));
+    GemmEpi f1; f1.bias = bfc1; f1.out = e->H16; f1.ldo = 4 * D;
+    TRY(gemm_plan_init(&L.fc1, e->Xn16, D, L.Wfc1, D, static_cast<int>(M), 4 * D, D, EPI_BIAS_GELU_F16, f1, pick_bn(4 * D)));
+    GemmEpi f2; f2.bias = bfc2; f2.gamma = ls2; f2.out = e->X; f2.ldo = D;
     TRY(gemm_plan_init(&L.fc2, e->H16, 4 * D, L.Wfc2, 4 * D, static_cast<int>(M), D, 4 * D, EPI_LS_RESID_F32, f2, pick_bn(D)));
   }
   if (e->w(enc + "norm.weight", D) == nullptr || e->w(enc + "norm.bias", D) == nullptr) return MHMR_ERR_STATE;
@@ -430,22 +396,15 @@ int run_plan(mhmr_engine* e, int cat, GemmPlan& plan, int M, cudaStream_t st) {
 int vit_forward(mhmr_engine* e, const float* x, int B, float* z_out, cudaStream_t st) {
   const int D = e->D, N = e->N, T = e->T, M = B * T;
   LAUNCH(MHMR_CAT_MISC, im2col_patch14(x, e->A16, B, e->cfg.img_size, 592, st));
-  if (e->fuse_ln) {
-    // the patch-embed epilogue writes X16 and the row statistics of the token rows; the cls rows come from here
-    LAUNCH(MHMR_CAT_MISC, cls_rows_stats(e->X, e->X16, e->statsB, e->stat_slots, e->cls_pos, B, T, D, st));
-  } else {
-    LAUNCH(MHMR_CAT_MISC, cls_rows(e->X, e->cls_pos, B, T, D, st));
-  }
+  LAUNCH(MHMR_CAT_MISC, cls_rows(e->X, e->cls_pos, B, T, D, st));
   TRY(run_plan(e, MHMR_CAT_GEMM_OTHER, e->patch_plan, B * N, st));
   for (int l = 0; l < e->depth; ++l) {
     VitLayer& L = e->vit[l];
-    if (!e->fuse_ln)
-      LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln1_g, L.ln1_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
+    LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln1_g, L.ln1_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
     TRY(run_plan(e, MHMR_CAT_GEMM_QKV, L.qkv, M, st));
     LAUNCH(MHMR_CAT_ATTENTION, attention_forward(e->QKV16, 3 * D, e->O16, D, B, T, D, st));
     TRY(run_plan(e, MHMR_CAT_GEMM_PROJ, L.proj, M, st));
-    if (!e->fuse_ln)
-      LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln2_g, L.ln2_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
+    LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln2_g, L.ln2_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
     TRY(run_plan(e, MHMR_CAT_GEMM_FC1, L.fc1, M, st));
     TRY(run_plan(e, MHMR_CAT_GEMM_FC2, L.fc2, M, st));
   }
@@ -545,7 +504,6 @@ int mhmr_create(const mhmr_config* cfg, mhmr_engine** out) {
   MHMR_REQUIRE(cfg->num_verts > 0, "num_verts must be positive");
   auto e = std::make_unique<mhmr_engine>();
   e->cfg = *cfg;
-  if (const char* f = std::getenv("MHMR_FUSE_LN")) e->fuse_ln = (f[0] != '0');
   const ArchSpec& a = kArch[cfg->arch];
   e->D = a.D; e->depth = a.depth; e->heads = a.heads;
   e->res = cfg->img_size / 14;

@@ -33,20 +33,6 @@ struct GemmEpi {
   int64_t ldo = 0;
   // Row remap: out_row = (m / rows_in) * rows_out + row_off + (m % rows_in); rows_in == 0 => identity.
   int rows_in = 0, rows_out = 0, row_off = 0;
-
-  // ---- LayerNorm fused across two GEMMs (optional; all null => plain epilogues) -----------------------
-  // Producer side (fp32 epilogues EPI_LS_RESID_F32 / EPI_ROWADD_F32): besides the fp32 result, write an
-  // fp16 copy (A operand of the next GEMM) and accumulate per-row (sum, sum of squares) of the result.
-  __half* out16 = nullptr;
-  int64_t ld16 = 0;
-  float* stats_out = nullptr;       // [out rows, stat_slots, 2]: one plain store per (row, epilogue-warp column slot)
-  int stat_slots = 0;               // == gemm_plan_stat_slots(producer plan)
-  // Consumer side (fp16 epilogues EPI_BIAS_F16 / EPI_BIAS_GELU_F16): the GEMM ran on the RAW rows x with
-  // W' = gamma (.) W, and LN(x) W^T + b == rstd * (acc - mu * colsum(W')) + (b + W beta) =: rstd*(..)+bias.
-  const float* ln_stats = nullptr;  // [M, ln_slots, 2] partial (sum, sum of squares) of the A rows
-  int ln_slots = 0;
-  const float* colsum = nullptr;    // [N] column sums of the fp16-rounded W'
-  float ln_inv_dim = 0.f, ln_eps = 0.f;
 };
 
 struct GemmPlan {
@@ -65,10 +51,5 @@ int gemm_plan_run(const GemmPlan* plan, cudaStream_t stream);
 int gemm_plan_run_2cta(const GemmPlan* plan, cudaStream_t stream);  // gemm_tc2.cu
 // launch geometry for `M` rows with this plan's tile shape
 int gemm_plan_grid(const GemmPlan* plan, int M);
-// number of per-row statistic slots a producer GEMM of width N with tile selector `bn` writes
-inline int gemm_stat_slots(int N, int bn) {
-  const int tile_n = (bn == 512) ? 256 : bn;
-  return ((N + tile_n - 1) / tile_n) * 2;  // two epilogue warps per TMEM lane quarter split the tile's columns
-}
 
 }  // namespace mhmr

@@ -210,8 +210,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_base = m_blk * BM2 + static_cast<int>(rank) * 128 + ew * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN2;
       constexpr int kChunksPerWarp = BN2 / 32 / (kEpiWarps2 / 4);
-      EpiTileCtx ctx;
-      epilogue_tile_begin<EPI>(ctx, ep, M, m_base, lane);
 #pragma unroll 1
       for (int ci = 0; ci < kChunksPerWarp; ++ci) {
         const int c = ci * (kEpiWarps2 / 4) + par;
@@ -227,9 +225,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         const int n0 = n_blk * BN2 + c * 32;
-        if (n0 < N) epilogue_chunk<EPI>(r, scratch, ep, ctx, M, N, m_base, n0, lane);
+        if (n0 < N) epilogue_chunk<EPI>(r, scratch, ep, M, N, m_base, n0, lane);
       }
-      epilogue_tile_end<EPI>(ctx, ep, M, m_base, n_blk * (kEpiWarps2 / 4) + par, lane);
     }
   }
 

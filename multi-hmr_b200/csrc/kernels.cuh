@@ -19,10 +19,6 @@ int f32_to_f16_2d(const float* src, int64_t lds, __half* dst, int64_t ldd, int r
                   cudaStream_t stream);
 int repack_f32(const float* src, int64_t lds, int scol, float* dst, int64_t ldd, int dcol, int rows,
                int cols, bool zero_fill, cudaStream_t stream);
-int fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K, __half* W16,
-            int64_t ldw16, float* colsum, float* bias_out, cudaStream_t stream);
-int cls_rows_stats(float* X, __half* X16, float* stats, int slots, const float* cls_pos, int B, int T, int D,
-                   cudaStream_t stream);
 int add_vec(const float* a, const float* b, float* out, int64_t n, int64_t b_period, cudaStream_t stream);
 
 // ---- head.cu ---------------------------------------------------------------------------------

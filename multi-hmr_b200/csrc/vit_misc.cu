@@ -232,76 +232,3 @@ int add_vec(const float* a, const float* b, float* out, int64_t n, int64_t b_per
   return MHMR_OK;
 }
 }  // namespace mhmr
-
-namespace mhmr {
-namespace {
-// LayerNorm folded into the following Linear (gemm_tc.cuh, GemmEpi::ln_stats): per output row n
-//   W16'[n, k] = fp16(W[n, k] * gamma[k]);  colsum[n] = sum_k float(W16'[n, k]);  bias'[n] = b[n] + sum_k W[n, k] beta[k]
-__global__ void fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, const float* __restrict__ bias, int K,
-                               __half* __restrict__ W16, int64_t ldw16, float* __restrict__ colsum,
-                               float* __restrict__ bias_out) {
-  const int n = blockIdx.x;
-  __shared__ float red[2][8];
-  float cs = 0.f, bb = 0.f;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const float w = W[static_cast<int64_t>(n) * K + k];
-    const __half h = __float2half_rn(w * gamma[k]);
-    W16[static_cast<int64_t>(n) * ldw16 + k] = h;
-    cs += __half2float(h);
-    bb += w * beta[k];
-  }
-  cs = warp_sum(cs);
-  bb = warp_sum(bb);
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = cs; red[1][threadIdx.x >> 5] = bb; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0.f, b = 0.f;
-    for (int w = 0; w < (blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
-    colsum[n] = a;
-    bias_out[n] = bias[n] + b;
-  }
-}
-
-// cls rows with the fused-LayerNorm by-products: fp32 row, fp16 copy, (sum, sum of squares) slots.
-__global__ void cls_row_stats_kernel(float* __restrict__ X, __half* __restrict__ X16, float* __restrict__ stats,
-                                     int slots, const float* __restrict__ cls_pos, int T, int D) {
-  const int b = blockIdx.x;
-  const int64_t row = static_cast<int64_t>(b) * T;
-  __shared__ float red[2][8];
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    const float v = cls_pos[i];
-    X[row * D + i] = v;
-    X16[row * D + i] = __float2half_rn(v);
-    s1 += v;
-    s2 += v * v;
-  }
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0.f, c = 0.f;
-    for (int w = 0; w < (blockDim.x >> 5); ++w) { a += red[0][w]; c += red[1][w]; }
-    float2* p = reinterpret_cast<float2*>(stats) + row * slots;  // slot 0 carries the totals
-    p[0] = make_float2(a, c);
-    for (int sl = 1; sl < slots; ++sl) p[sl] = make_float2(0.f, 0.f);
-  }
-}
-}  // namespace
-
-int fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K, __half* W16,
-            int64_t ldw16, float* colsum, float* bias_out, cudaStream_t stream) {
-  fold_ln_kernel<<<N, 256, 0, stream>>>(W, gamma, beta, bias, K, W16, ldw16, colsum, bias_out);
-  MHMR_CUDA_CHECK(cudaGetLastError());
-  return MHMR_OK;
-}
-
-int cls_rows_stats(float* X, __half* X16, float* stats, int slots, const float* cls_pos, int B, int T, int D,
-                   cudaStream_t stream) {
-  cls_row_stats_kernel<<<B, 256, 0, stream>>>(X, X16, stats, slots, cls_pos, T, D);
-  MHMR_CUDA_CHECK(cudaGetLastError());
-  return MHMR_OK;
-}
-}  // namespace mhmr

@@ -100,8 +100,7 @@ def test_batch_invariance_and_smaller_batches(cuda_device):
 
 
 def test_forward_is_bit_reproducible(cuda_device):
-    """No atomics on the data path (the fused-LayerNorm row statistics are per-slot plain stores summed in a
-    fixed order): the same inputs give the same bits, like the reference on CPU."""
+    """No atomics on the data path: the same inputs give the same bits run after run, like the reference on CPU."""
     case, sd, bm, x, K, idx = pu.build_inputs("s_224_S_forced")
     m = pu.build_engine(case, sd, bm)
     a = {k: v.clone() for k, v in m(x, idx=idx, K=K, is_training=True).items()}
@@ -109,25 +108,6 @@ def test_forward_is_bit_reproducible(cuda_device):
         b = m(x, idx=idx, K=K, is_training=True)
         for k in ("scores", "v3d", "rotmat", "shape", "dist", "loc", "j2d"):
             assert torch.equal(a[k], b[k]), k
-
-
-def test_fused_layernorm_matches_separate_kernel(cuda_device, monkeypatch):
-    """LayerNorm folded into the qkv / fc1 GEMM epilogues (engine default) vs the stand-alone LayerNorm
-    kernel (MHMR_FUSE_LN=0): same maths up to one fp16 operand rounding, and both within the parity bar."""
-    case, sd, bm, x, K, idx = pu.build_inputs("s_448_B_forced")
-    gold = pu.load_golden("s_448_B_forced")
-    outs = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("MHMR_FUSE_LN", mode)
-        m = pu.build_engine(case, sd, bm)
-        out = m(x, idx=idx, K=K, is_training=True)
-        bad = pu.compare(out, gold, [k for k in gold if k != "idx"], focal=float(K[:, 0, 0].max()))
-        assert not bad, (mode, bad)
-        outs[mode] = {k: out[k].clone() for k in ("v3d", "scores", "shape")}
-        z = m.backbone(x)
-        outs[mode]["z"] = z.clone()
-    assert (outs["1"]["z"] - outs["0"]["z"]).abs().max().item() <= 2e-2 * outs["0"]["z"].abs().max().item()
-    assert (outs["1"]["v3d"] - outs["0"]["v3d"]).abs().max().item() <= 1e-3
 
 
 def _oracle_cpu(sd, bm, backbone, S, x, K, num_betas=10, **kw):
