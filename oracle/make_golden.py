@@ -37,6 +37,9 @@ CASES = {
                            jitter=True),
     "s_224_S_asymK": dict(backbone="dinov2_vits14", img_size=224, batch=2, persons=[2, 2], seed=4, jitter=True,
                           asymmetric=True),
+    # the ViT-L architecture (depth 24, 16 heads, D = 1024) of the headline configs, at a size the CPU reference
+    # runs in seconds; rectangular per-image intrinsics
+    "s_280_L_forced": dict(backbone="dinov2_vitl14", img_size=280, batch=2, persons=[2, 1], seed=5, jitter=True),
 }
 
 _CURRENT_BM = {}
