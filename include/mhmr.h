@@ -78,6 +78,7 @@ typedef struct mhmr_config {
   int num_betas;         /* Model(num_betas=...)     model.py:47 (10 or 11) */
   int person_center_idx; /* index of Model(person_center=...) in smplx JOINT_NAMES ('head' = 15) */
   int num_verts;         /* body-model vertices (SMPL-X: 10475) */
+  int refine_central;    /* 1: fp32 refinement of the detected tokens' residual streams; 0: bulk fp16 pass only */
 } mhmr_config;
 
 /* Per-call outputs: device buffers owned by the caller (torch tensors), sized for max_persons.
@@ -142,6 +143,28 @@ int mhmr_smplx_forward(mhmr_engine* h, int P, const float* rotvec, const float* 
                        const float* expression, const float* loc, const float* dist, const float* K_det,
                        float* v3d, float* v2d, float* j3d, float* j2d, float* transl, float* transl_pelvis,
                        void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Sharded batches (one process per GPU, image shards per rank).  The reference is single-GPU
+ * (README.md:107); these entry points are what a multi-GPU caller of `forward_model` binds.
+ *   block  = header (8 x int32: persons detected, persons packed, capacity, floats per record, first global
+ *            image index of the rank, 0, 0, 0) | capacity x record (fp32)
+ *   record = [global image index, score, loc 2, transl 3, transl_pelvis 3, rotvec 159, expression 10,
+ *             shape nb, v3d 3V, j3d 381, j2d 254]  — the person dict of model.py:329-347
+ * ---------------------------------------------------------------------------------------------- */
+int mhmr_record_floats(int num_betas, int num_verts);
+int64_t mhmr_record_block_bytes(int num_betas, int num_verts, int capacity);
+/* ONE kernel: packs the (device-resident) outputs of a forward into `block`; the person count is read on the
+ * device and travels in the header, unused record slots are zero-filled. */
+int mhmr_pack_records(const mhmr_outputs* out, int max_persons, int num_betas, int num_verts, int image_offset,
+                      int capacity, float* block, void* stream);
+/* NCCL communicator of the record exchange (libnccl.so.2 is resolved at run time from the process). */
+typedef struct mhmr_comm mhmr_comm;
+int mhmr_nccl_unique_id(void* id128);                                   /* ncclGetUniqueId (rank 0) */
+int mhmr_comm_create(const void* id128, int world, int rank, mhmr_comm** out);  /* ncclCommInitRank  */
+int mhmr_comm_destroy(mhmr_comm* c);
+/* ONE ncclAllGather of the per-rank blocks (all_blocks = world x block_bytes, rank order) on `stream`. */
+int mhmr_allgather_records(mhmr_comm* c, const void* block, void* all_blocks, int64_t block_bytes, void* stream);
+
 /* Kernel launches enqueued by the last mhmr_forward (bench.py's `gpu_launches`). */
 int mhmr_last_launch_count(mhmr_engine* h);
 
@@ -158,7 +181,8 @@ int mhmr_last_launch_count(mhmr_engine* h);
 #define MHMR_CAT_GEMM_OTHER 7  /* patch-embed, detection hidden, HPH to_kv */
 #define MHMR_CAT_HEAD 8        /* detection / HPH / post-processing kernels */
 #define MHMR_CAT_SMPLX 9       /* prep + vertex + joints kernels            */
-#define MHMR_NUM_CATEGORIES 10
+#define MHMR_CAT_REFINE 10     /* fp32 refinement of the detected tokens' residual streams */
+#define MHMR_NUM_CATEGORIES 11
 int mhmr_set_profiling(mhmr_engine* h, int enable);
 int mhmr_get_profile(mhmr_engine* h, float* ms_by_category, int* launches_by_category);
 

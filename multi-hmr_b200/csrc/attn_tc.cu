@@ -513,10 +513,9 @@ template <int kAb>
 int attn_launch(const AttnArgs& a) {
   constexpr int smem = attn_smem_bytes(kStagesK, kStagesV);
   auto kern = attn_fwd_kernel<kStagesK, kStagesV, kAb>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = a.grid;

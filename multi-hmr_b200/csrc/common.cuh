@@ -57,6 +57,12 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, CUtensorMapDataType dtype, 
                  uint32_t box_cols, bool swizzle128);
 
 int device_sm_count();
+// Function attributes (cudaFuncSetAttribute) and the SM count are per DEVICE: `first()` is true the first time
+// it is asked on the current device, so that a process with engines on several GPUs configures each of them.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first();
+};
 // Programmatic dependent launch for the back-to-back kernels of the ViT loop (MHMR_PDL=0 disables).
 bool pdl_enabled();
 

@@ -32,6 +32,8 @@ constexpr int kCamDim = 99;
 struct VitLayer {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bproj, *ls1, *bfc1, *bfc2, *ls2;
   __half *Wqkv, *Wproj, *Wfc1, *Wfc2;
+  const float *Wproj32, *Wfc1_32, *Wfc2_32;  // fp32 masters (central-stream refinement)
+  __half* O16;                               // this layer's attention output [max_batch*T, D]
   GemmPlan qkv, proj, fc1, fc2;
 };
 struct HphLayer {
@@ -83,6 +85,10 @@ struct mhmr_engine {
   __half *A16 = nullptr, *Xn16 = nullptr, *QKV16 = nullptr, *O16 = nullptr, *H16 = nullptr, *ctx16 = nullptr;
   float *X = nullptr, *z32 = nullptr, *scores_raw = nullptr, *KV32 = nullptr, *Kinv = nullptr;
   int *det = nullptr, *count = nullptr, *img_off = nullptr;
+  // central-stream refinement: token rows, input patches, residual streams and MLP hidden of the detected persons
+  int* r_rowidx = nullptr;
+  float *r_patch = nullptr, *r_x = nullptr, *r_h = nullptr;
+  const float* Wpatch32 = nullptr;
   float *zc = nullptr, *query = nullptr, *vals = nullptr, *dKV = nullptr, *offh = nullptr, *xa = nullptr,
         *qkvp = nullptr, *att = nullptr, *qca = nullptr, *ffh = nullptr, *dec = nullptr, *K_det = nullptr,
         *one_count_x = nullptr;
@@ -159,6 +165,7 @@ int finalize_vit(mhmr_engine* e, cudaStream_t st) {
     return MHMR_ERR_STATE;
   }
   TRY(to_f16(e, pw, 588, D, 588, 592, &e->Wpatch, st));
+  e->Wpatch32 = pw;
   TRY(e->alloc(&e->rowadd, static_cast<size_t>(N) * D));
   TRY(add_vec(pos + D, pb, e->rowadd, static_cast<int64_t>(N) * D, D, st));
   TRY(e->alloc(&e->cls_pos, D));
@@ -169,7 +176,9 @@ int finalize_vit(mhmr_engine* e, cudaStream_t st) {
   TRY(e->alloc(&e->X, M * D));
   TRY(e->alloc(&e->Xn16, M * D));
   TRY(e->alloc(&e->QKV16, M * 3 * D));
-  TRY(e->alloc(&e->O16, M * D));
+  // one attention-output buffer per layer when the refinement pass needs the rows of every layer afterwards
+  const size_t o_layers = e->cfg.refine_central ? static_cast<size_t>(e->depth) : 1;
+  TRY(e->alloc(&e->O16, o_layers * M * D));
   TRY(e->alloc(&e->H16, M * 4 * D));
 
   GemmEpi ep;
@@ -188,6 +197,8 @@ int finalize_vit(mhmr_engine* e, cudaStream_t st) {
     NEEDW(wfc1, b + "mlp.fc1.weight", 4ll * D * D) NEEDW(bfc1, b + "mlp.fc1.bias", 4 * D)
     NEEDW(wfc2, b + "mlp.fc2.weight", 4ll * D * D) NEEDW(bfc2, b + "mlp.fc2.bias", D)
     L.ln1_g = n1g; L.ln1_b = n1b; L.ln2_g = n2g; L.ln2_b = n2b;
+    L.Wproj32 = wproj; L.Wfc1_32 = wfc1; L.Wfc2_32 = wfc2;
+    L.O16 = e->O16 + (e->cfg.refine_central ? static_cast<size_t>(l) * M * D : 0);
     L.bqkv = bqkv; L.bproj = bproj; L.ls1 = ls1; L.bfc1 = bfc1; L.bfc2 = bfc2; L.ls2 = ls2;
     TRY(to_f16(e, wqkv, D, 3 * D, D, D, &L.Wqkv, st));
     TRY(to_f16(e, wproj, D, D, D, D, &L.Wproj, st));
@@ -196,7 +207,7 @@ int finalize_vit(mhmr_engine* e, cudaStream_t st) {
     GemmEpi a; a.bias = bqkv; a.out = e->QKV16; a.ldo = 3 * D;
     TRY(gemm_plan_init(&L.qkv, e->Xn16, D, L.Wqkv, D, static_cast<int>(M), 3 * D, D, EPI_BIAS_F16, a, pick_bn(3 * D)));
     GemmEpi p; p.bias = bproj; p.gamma = ls1; p.out = e->X; p.ldo = D;
-    TRY(gemm_plan_init(&L.proj, e->O16, D, L.Wproj, D, static_cast<int>(M), D, D, EPI_LS_RESID_F32, p, pick_bn(D)));
+    TRY(gemm_plan_init(&L.proj, L.O16, D, L.Wproj, D, static_cast<int>(M), D, D, EPI_LS_RESID_F32, p, pick_bn(D)));
     GemmEpi f1; f1.bias = bfc1; f1.out = e->H16; f1.ldo = 4 * D;
     TRY(gemm_plan_init(&L.fc1, e->Xn16, D, L.Wfc1, D, static_cast<int>(M), 4 * D, D, EPI_BIAS_GELU_F16, f1, pick_bn(4 * D)));
     GemmEpi f2; f2.bias = bfc2; f2.gamma = ls2; f2.out = e->X; f2.ldo = D;
@@ -319,6 +330,12 @@ int finalize_head(mhmr_engine* e, cudaStream_t st) {
   TRY(e->alloc(&e->ffh, static_cast<size_t>(Pm) * kHphDim));
   TRY(e->alloc(&e->dec, static_cast<size_t>(Pm) * e->ndec));
   TRY(e->alloc(&e->K_det, static_cast<size_t>(Pm) * 9));
+  if (e->cfg.refine_central) {
+    TRY(e->alloc(&e->r_rowidx, Pm));
+    TRY(e->alloc(&e->r_patch, static_cast<size_t>(Pm) * 592));
+    TRY(e->alloc(&e->r_x, static_cast<size_t>(Pm) * D));
+    TRY(e->alloc(&e->r_h, static_cast<size_t>(Pm) * 4 * D));
+  }
   return MHMR_OK;
 }
 
@@ -402,7 +419,7 @@ int vit_forward(mhmr_engine* e, const float* x, int B, float* z_out, cudaStream_
     VitLayer& L = e->vit[l];
     LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln1_g, L.ln1_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
     TRY(run_plan(e, MHMR_CAT_GEMM_QKV, L.qkv, M, st));
-    LAUNCH(MHMR_CAT_ATTENTION, attention_forward(e->QKV16, 3 * D, e->O16, D, B, T, D, st));
+    LAUNCH(MHMR_CAT_ATTENTION, attention_forward(e->QKV16, 3 * D, L.O16, D, B, T, D, st));
     TRY(run_plan(e, MHMR_CAT_GEMM_PROJ, L.proj, M, st));
     LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln2_g, L.ln2_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
     TRY(run_plan(e, MHMR_CAT_GEMM_FC1, L.fc1, M, st));
@@ -417,7 +434,38 @@ int vit_forward(mhmr_engine* e, const float* x, int B, float* z_out, cudaStream_
   return MHMR_OK;
 }
 
-int head_forward(mhmr_engine* e, const float* K, int B, float det_thresh, int nms, const int64_t* forced_idx,
+// Central-stream refinement.  The bulk pass computes every token with fp16 tensor-core operands;
+// what the per-person outputs are sensitive to is the residual stream of the DETECTED tokens themselves (their
+// own patch embedding and their own MLP / projection branches: 92 % of the feature error variance,
+// tools/precision_study.py).  Those few rows are recomputed here in fp32 with the fp32 master weights:
+//   x = patch-embed(pixels) + pos;  per block: x += ls1 * (Wproj . O16[row] + b);  x += ls2 * MLP(LN2(x))
+// where O16[row] is the attention output of the bulk pass for that token (kept per layer).  The final norm is
+// applied by person_gather.  Same arithmetic as dinov2 Block.forward (reached from blocks/dinov2.py:25).
+int refine_streams(mhmr_engine* e, const float* x, const int* det_b, const int* det_y, const int* det_x,
+                   const int* count, cudaStream_t st) {
+  const int D = e->D, Pm = e->cfg.max_persons;
+  LAUNCH(MHMR_CAT_REFINE, refine_prepare(x, e->cfg.img_size, e->rowadd, D, det_b, det_y, det_x, count, Pm, e->res,
+                                         e->r_rowidx, e->r_patch, 592, e->r_x, st));
+  SkinnyExtra none;
+  LAUNCH(MHMR_CAT_REFINE, skinny_linear_ex(e->r_patch, 592, none, count, Pm, 588, e->Wpatch32, 588, nullptr, D, nullptr,
+                                           nullptr, 0.f, 0, e->r_x, D, e->r_x, D, st));
+  for (int l = 0; l < e->depth; ++l) {
+    VitLayer& L = e->vit[l];
+    SkinnyExtra po;
+    po.x16 = L.O16; po.ldx16 = D; po.rowidx = e->r_rowidx; po.gamma = L.ls1;
+    LAUNCH(MHMR_CAT_REFINE, skinny_linear_ex(nullptr, 0, po, count, Pm, D, L.Wproj32, D, L.bproj, D, nullptr, nullptr, 0.f,
+                                             0, e->r_x, D, e->r_x, D, st));
+    LAUNCH(MHMR_CAT_REFINE, skinny_linear_ex(e->r_x, D, none, count, Pm, D, L.Wfc1_32, D, L.bfc1, 4 * D, L.ln2_g, L.ln2_b,
+                                             1e-6f, 2, nullptr, 0, e->r_h, 4 * D, st));
+    SkinnyExtra f2;
+    f2.gamma = L.ls2;
+    LAUNCH(MHMR_CAT_REFINE, skinny_linear_ex(e->r_h, 4 * D, f2, count, Pm, 4 * D, L.Wfc2_32, 4 * D, L.bfc2, D, nullptr,
+                                             nullptr, 0.f, 0, e->r_x, D, e->r_x, D, st));
+  }
+  return MHMR_OK;
+}
+
+int head_forward(mhmr_engine* e, const float* x, const float* K, int B, float det_thresh, int nms, const int64_t* forced_idx,
                  int forced_P, const mhmr_outputs* o, cudaStream_t st) {
   const int D = e->D, N = e->N, res = e->res, Pm = e->cfg.max_persons, Cq = e->Cq, nb = e->cfg.num_betas;
   const int heads = e->cfg.xat_num_heads, inner = heads * 32, BN = B * N;
@@ -440,7 +488,13 @@ int head_forward(mhmr_engine* e, const float* K, int B, float det_thresh, int nm
   // keys / values of both decoder layers for every token (to_kv, cross_attn_transformer.py:187)
   TRY(run_plan(e, MHMR_CAT_GEMM_OTHER, e->kv_plan, BN, st));
   const std::string h = "x_attention_head.";
-  LAUNCH(MHMR_CAT_HEAD, person_gather(e->z32, e->Kinv, e->w("camera.freq_bands"), e->w(h + "cross_queries_x"),
+  const float* xr = nullptr;
+  if (e->cfg.refine_central) {
+    TRY(refine_streams(e, x, det_b, det_y, det_x, count, st));
+    xr = e->r_x;
+  }
+  LAUNCH(MHMR_CAT_HEAD, person_gather(e->z32, xr, e->w("backbone.encoder.norm.weight"), e->w("backbone.encoder.norm.bias"),
+                       e->Kinv, e->w("camera.freq_bands"), e->w(h + "cross_queries_x"),
                        e->w(h + "cross_queries_y"), e->w(h + "cross_values_x"), e->w(h + "cross_values_y"),
                        det_b, det_y, det_x, count, Pm, res, D, e->zc, e->query, e->vals, Cq, st));
   // offset head (model.py:258)
@@ -577,7 +631,7 @@ int mhmr_forward(mhmr_engine* h, const float* x, const float* K, int B, float de
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   h->launches = 0;
   TRY(vit_forward(h, x, B, out->z, st));
-  return head_forward(h, K, B, det_thresh, nms_kernel_size, forced_idx, forced_P, out, st);
+  return head_forward(h, x, K, B, det_thresh, nms_kernel_size, forced_idx, forced_P, out, st);
 }
 
 int mhmr_sync_count(mhmr_engine* h, void* stream, int* num_persons) {

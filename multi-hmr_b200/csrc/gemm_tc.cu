@@ -175,11 +175,10 @@ template <int BN, int EPI>
 int launch_one(const GemmPlan* p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tc_kernel<BN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p->grid);

@@ -241,10 +241,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int EPI>
 int launch_2cta(const GemmPlan* p, cudaStream_t stream) {
   auto kern = gemm_tc2_kernel<EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p->grid);

@@ -213,32 +213,89 @@ __global__ void ctx_fourier_kernel(const float* __restrict__ Kinv, const float* 
   ctx[static_cast<int64_t>(row) * ld + D + j] = __float2half_rn(v);
 }
 
-// Per person: z_central (fp32 gather), query = cat(z_central, z_K) + cross_queries_x[y] + cross_queries_y[x]
+// Block-wide sum over 256 threads (all threads receive the result).
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+// Per person: z_central, query = cat(z_central, z_K) + cross_queries_x[y] + cross_queries_y[x]
 // (model.py:252-265, :500-504; note queries_x is indexed with y and queries_y with x, as in the reference),
 // and the learned value embedding that the reference adds into the context at this cell (model.py:514-517).
-__global__ void person_gather_kernel(const float* __restrict__ z32, const float* __restrict__ Kinv,
-                                     const float* __restrict__ freqs, const float* __restrict__ cq_x,
-                                     const float* __restrict__ cq_y, const float* __restrict__ cv_x,
-                                     const float* __restrict__ cv_y, const int* __restrict__ det_b,
-                                     const int* __restrict__ det_y, const int* __restrict__ det_x,
-                                     const int* __restrict__ count, int res, int D, float* __restrict__ zc,
-                                     float* __restrict__ query, float* __restrict__ vals, int ldq) {
+// z_central is either the fp32 feature row of the bulk pass (z32) or, when `xr` is given, the final LayerNorm
+// (eps 1e-6) of the person's REFINED residual stream (central-stream refinement, refine_* below).
+__global__ void __launch_bounds__(256)
+person_gather_kernel(const float* __restrict__ z32, const float* __restrict__ xr,
+                     const float* __restrict__ norm_g, const float* __restrict__ norm_b,
+                     const float* __restrict__ Kinv, const float* __restrict__ freqs,
+                     const float* __restrict__ cq_x, const float* __restrict__ cq_y,
+                     const float* __restrict__ cv_x, const float* __restrict__ cv_y,
+                     const int* __restrict__ det_b, const int* __restrict__ det_y,
+                     const int* __restrict__ det_x, const int* __restrict__ count, int res, int D,
+                     float* __restrict__ zc, float* __restrict__ query, float* __restrict__ vals, int ldq) {
+  __shared__ float red[8];
   const int p = blockIdx.x;
   if (p >= *count) return;
   const int b = det_b[p], y = det_y[p], x = det_x[p];
   const int N = res * res, C = D + 99;
   const float* zr = z32 + (static_cast<int64_t>(b) * N + y * res + x) * D;
+  float mean = 0.f, rstd = 1.f;
+  if (xr != nullptr) {
+    const float* r = xr + static_cast<int64_t>(p) * D;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < D; c += 256) s += r[c];
+    mean = block_sum_256(s, red) / D;
+    float q = 0.f;
+    for (int c = threadIdx.x; c < D; c += 256) { const float d = r[c] - mean; q += d * d; }
+    rstd = rsqrtf(block_sum_256(q, red) / D + 1e-6f);
+  }
   for (int c = threadIdx.x; c < ldq; c += blockDim.x) {
     float v = 0.f, val = 0.f;
     if (c < C) {
-      const float base = (c < D) ? zr[c] : camera_feature(Kinv + b * 9, freqs, y, x, c - D);
-      if (c < D) zc[static_cast<int64_t>(p) * D + c] = base;
+      float base;
+      if (c < D) {
+        base = (xr != nullptr) ? (xr[static_cast<int64_t>(p) * D + c] - mean) * rstd * norm_g[c] + norm_b[c] : zr[c];
+        zc[static_cast<int64_t>(p) * D + c] = base;
+      } else {
+        base = camera_feature(Kinv + b * 9, freqs, y, x, c - D);
+      }
       v = base + cq_x[static_cast<int64_t>(y) * C + c] + cq_y[static_cast<int64_t>(x) * C + c];
       val = cv_x[static_cast<int64_t>(y) * C + c] + cv_y[static_cast<int64_t>(x) * C + c];
     }
     query[static_cast<int64_t>(p) * ldq + c] = v;
     vals[static_cast<int64_t>(p) * ldq + c] = val;
   }
+}
+
+// Central-stream refinement, step 0: per detected person, the token row index of its cell in the [B*T, .]
+// token matrices (cls row skipped), its 14x14x3 input patch in the order of the patch-embed weight
+// (c, ky, kx: dinov2 PatchEmbed Conv2d) and the fp32 (pos_embed + bias) row of its cell.
+__global__ void __launch_bounds__(256)
+refine_prepare_kernel(const float* __restrict__ img, int S, const float* __restrict__ rowadd, int D,
+                      const int* __restrict__ det_b, const int* __restrict__ det_y,
+                      const int* __restrict__ det_x, const int* __restrict__ count, int res,
+                      int* __restrict__ rowidx, float* __restrict__ patch, int ldp, float* __restrict__ xr) {
+  const int p = blockIdx.x;
+  if (p >= *count) return;
+  const int b = det_b[p], y = det_y[p], x = det_x[p];
+  const int N = res * res, n = y * res + x;
+  if (threadIdx.x == 0) rowidx[p] = b * (N + 1) + 1 + n;
+  const float* im = img + static_cast<int64_t>(b) * 3 * S * S;
+  for (int k = threadIdx.x; k < ldp; k += 256) {
+    float v = 0.f;
+    if (k < 588) {
+      const int c = k / 196, r = k - c * 196, ky = r / 14, kx = r - ky * 14;
+      v = im[(static_cast<int64_t>(c) * S + y * 14 + ky) * S + x * 14 + kx];
+    }
+    patch[static_cast<int64_t>(p) * ldp + k] = v;
+  }
+  for (int c = threadIdx.x; c < D; c += 256) xr[static_cast<int64_t>(p) * D + c] = rowadd[static_cast<int64_t>(n) * D + c];
 }
 
 // KV[b*N + cell(p), :] += dKV[p, :]   (context += learned values at detected cells, model.py:517)
@@ -253,18 +310,21 @@ __global__ void kv_add_rows_kernel(float* __restrict__ KV, int64_t ldkv, const f
 }
 
 // ----------------------------------------------------------------------------------------------
-// Skinny linear: out[p, n] = resid[p, n] + act( LN?(x[p, :]) . W[n, :] + bias[n] ),  p < *count.
-// fp32 weights streamed once per chunk of 8 persons (from L2 after the first chunk).
-// grid = (ceil(Nout / 32), ceil(max_persons / 8)), block = 256.
+// Skinny linear: out[p, n] = resid[p, n] + gamma[n] * act( LN?(x[p, :]) . W[n, :] + bias[n] ),  p < *count.
+// fp32 weights streamed once per chunk of 8 persons (from L2 after the first chunk).  The input rows are
+// either fp32 rows of `x` or fp16 rows `x16[rowidx[p], :]` gathered from a token matrix (central-stream
+// refinement: rows of the attention output of the backbone's bulk pass).
+// grid = (ceil(Nout / cols), ceil(max_persons / 8)), block = 256.
 // ----------------------------------------------------------------------------------------------
 constexpr int kSkinnyPT = 8;
-constexpr int kSkinnyCols = 32;
 
 __global__ void __launch_bounds__(256)
-skinny_linear_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ count, int K,
+skinny_linear_kernel(const float* __restrict__ x, int ldx, const __half* __restrict__ x16, int64_t ldx16,
+                     const int* __restrict__ rowidx, const int* __restrict__ count, int K,
                      const float* __restrict__ W, int ldw, const float* __restrict__ bias, int Nout,
                      const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps, int act,
-                     const float* __restrict__ resid, int ldr, float* __restrict__ out, int ldo) {
+                     const float* __restrict__ gamma, const float* __restrict__ resid, int ldr,
+                     float* __restrict__ out, int ldo, int cols) {
   extern __shared__ float xs[];  // [kSkinnyPT][Kp], Kp = K rounded up to 4
   const int P = *count;
   const int p0 = blockIdx.y * kSkinnyPT;
@@ -277,12 +337,21 @@ skinny_linear_kernel(const float* __restrict__ x, int ldx, const int* __restrict
   {
     float* dst = xs + warp * Kp;
     if (warp < np) {
-      const float* src = x + static_cast<int64_t>(p0 + warp) * ldx;
       float s = 0.f;
-      for (int k = lane; k < Kp; k += 32) {
-        const float v = (k < K) ? src[k] : 0.f;
-        dst[k] = v;
-        s += v;
+      if (x16 != nullptr) {
+        const __half* src = x16 + static_cast<int64_t>(rowidx[p0 + warp]) * ldx16;
+        for (int k = lane; k < Kp; k += 32) {
+          const float v = (k < K) ? __half2float(src[k]) : 0.f;
+          dst[k] = v;
+          s += v;
+        }
+      } else {
+        const float* src = x + static_cast<int64_t>(p0 + warp) * ldx;
+        for (int k = lane; k < Kp; k += 32) {
+          const float v = (k < K) ? src[k] : 0.f;
+          dst[k] = v;
+          s += v;
+        }
       }
       if (ln_g != nullptr) {
         const float mean = warp_sum(s) / K;
@@ -297,8 +366,8 @@ skinny_linear_kernel(const float* __restrict__ x, int ldx, const int* __restrict
   }
   __syncthreads();
 
-  for (int c = warp; c < kSkinnyCols; c += 8) {
-    const int n = blockIdx.x * kSkinnyCols + c;
+  for (int c = warp; c < cols; c += 8) {
+    const int n = blockIdx.x * cols + c;
     if (n >= Nout) break;
     const float* wr = W + static_cast<int64_t>(n) * ldw;
     float acc[kSkinnyPT];
@@ -321,6 +390,7 @@ skinny_linear_kernel(const float* __restrict__ x, int ldx, const int* __restrict
       if (bias != nullptr) v += bias[n];
       if (act == 1) v = fmaxf(v, 0.f);
       if (act == 2) v = gelu_erf(v);
+      if (gamma != nullptr) v *= gamma[n];
       if (resid != nullptr) v += resid[static_cast<int64_t>(p0 + lane) * ldr + n];
       out[static_cast<int64_t>(p0 + lane) * ldo + n] = v;
     }
@@ -601,12 +671,22 @@ int ctx_fourier(const float* Kinv, const float* freqs, __half* ctx, int64_t ld, 
   return MHMR_OK;
 }
 
-int person_gather(const float* z32, const float* Kinv, const float* freqs, const float* cq_x,
-                  const float* cq_y, const float* cv_x, const float* cv_y, const int* det_b,
-                  const int* det_y, const int* det_x, const int* count, int max_persons, int res, int D,
-                  float* zc, float* query, float* vals, int ldq, cudaStream_t st) {
-  person_gather_kernel<<<max_persons, 256, 0, st>>>(z32, Kinv, freqs, cq_x, cq_y, cv_x, cv_y, det_b, det_y,
-                                                    det_x, count, res, D, zc, query, vals, ldq);
+int person_gather(const float* z32, const float* xr, const float* norm_g, const float* norm_b, const float* Kinv,
+                  const float* freqs, const float* cq_x, const float* cq_y, const float* cv_x, const float* cv_y,
+                  const int* det_b, const int* det_y, const int* det_x, const int* count, int max_persons, int res,
+                  int D, float* zc, float* query, float* vals, int ldq, cudaStream_t st) {
+  person_gather_kernel<<<max_persons, 256, 0, st>>>(z32, xr, norm_g, norm_b, Kinv, freqs, cq_x, cq_y, cv_x, cv_y,
+                                                    det_b, det_y, det_x, count, res, D, zc, query, vals, ldq);
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+int refine_prepare(const float* img, int S, const float* rowadd, int D, const int* det_b, const int* det_y,
+                   const int* det_x, const int* count, int max_persons, int res, int* rowidx, float* patch,
+                   int ldp, float* xr, cudaStream_t st) {
+  MHMR_REQUIRE(ldp >= 588 && ldp % 4 == 0, "refine_prepare: patch pitch must be >= 588 and a multiple of 4");
+  refine_prepare_kernel<<<max_persons, 256, 0, st>>>(img, S, rowadd, D, det_b, det_y, det_x, count, res, rowidx,
+                                                     patch, ldp, xr);
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }
@@ -618,24 +698,40 @@ int kv_add_rows(float* KV, int64_t ldkv, const float* dKV, int ncols, const int*
   return MHMR_OK;
 }
 
+int skinny_linear_ex(const float* x, int ldx, const SkinnyExtra& ex, const int* count, int max_persons, int K,
+                     const float* W, int ldw, const float* bias, int Nout, const float* ln_g, const float* ln_b,
+                     float ln_eps, int act, const float* resid, int ldr, float* out, int ldo, cudaStream_t st) {
+  MHMR_REQUIRE(ldw % 4 == 0 && ldw >= ((K + 3) & ~3), "skinny_linear: weight pitch must be >= K rounded to 4");
+  MHMR_REQUIRE((x != nullptr) != (ex.x16 != nullptr), "skinny_linear: exactly one of x / x16");
+  MHMR_REQUIRE(ex.x16 == nullptr || ex.rowidx != nullptr, "skinny_linear: x16 needs row indices");
+  const int Kp = (K + 3) & ~3;
+  const size_t smem = static_cast<size_t>(kSkinnyPT) * Kp * sizeof(float);
+  constexpr size_t kMaxSmem = 200 * 1024;
+  static PerDeviceOnce once;
+  if (once.first()) {
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kMaxSmem)));
+  }
+  MHMR_REQUIRE(smem <= kMaxSmem, "skinny_linear: K too large");
+  // columns per CTA: 32 by default; fewer when that leaves most SMs without work (weight streaming is the cost)
+  int cols = ex.cols > 0 ? ex.cols : 32;
+  if (ex.cols <= 0) {
+    while (cols > 8 && (Nout + cols - 1) / cols < 2 * device_sm_count()) cols >>= 1;
+  }
+  dim3 grid((Nout + cols - 1) / cols, (max_persons + kSkinnyPT - 1) / kSkinnyPT);
+  skinny_linear_kernel<<<grid, 256, smem, st>>>(x, ldx, ex.x16, ex.ldx16, ex.rowidx, count, K, W, ldw, bias, Nout,
+                                                ln_g, ln_b, ln_eps, act, ex.gamma, resid, ldr, out, ldo, cols);
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
 int skinny_linear(const float* x, int ldx, const int* count, int max_persons, int K, const float* W, int ldw,
                   const float* bias, int Nout, const float* ln_g, const float* ln_b, float ln_eps, int act,
                   const float* resid, int ldr, float* out, int ldo, cudaStream_t st) {
-  MHMR_REQUIRE(ldw % 4 == 0 && ldw >= ((K + 3) & ~3), "skinny_linear: weight pitch must be >= K rounded to 4");
-  const int Kp = (K + 3) & ~3;
-  const size_t smem = static_cast<size_t>(kSkinnyPT) * Kp * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         96 * 1024));
-    attr_set = true;
-  }
-  MHMR_REQUIRE(smem <= 96 * 1024, "skinny_linear: K too large");
-  dim3 grid((Nout + kSkinnyCols - 1) / kSkinnyCols, (max_persons + kSkinnyPT - 1) / kSkinnyPT);
-  skinny_linear_kernel<<<grid, 256, smem, st>>>(x, ldx, count, K, W, ldw, bias, Nout, ln_g, ln_b, ln_eps, act,
-                                                resid, ldr, out, ldo);
-  MHMR_CUDA_CHECK(cudaGetLastError());
-  return MHMR_OK;
+  SkinnyExtra ex;
+  ex.cols = 32;
+  return skinny_linear_ex(x, ldx, ex, count, max_persons, K, W, ldw, bias, Nout, ln_g, ln_b, ln_eps, act, resid, ldr,
+                          out, ldo, st);
 }
 
 int hph_self_attn(const float* qkv, int ld, const int* det_b, const int* img_off, const int* count,

@@ -66,15 +66,23 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, CUtensorMapDataType dtype, 
   return MHMR_OK;
 }
 
+bool PerDeviceOnce::first() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
+  static int sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    if (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0)
+      sms[dev] = 148;
   }
-  return sms;
+  return sms[dev];
 }
 
 bool pdl_enabled() {

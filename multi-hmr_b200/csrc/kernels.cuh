@@ -35,15 +35,31 @@ int loc_to_transl(const float* loc, const float* dist, const float* K_det, int P
 int invert_K(const float* K, float* Kinv, int B, cudaStream_t st);
 int ctx_fourier(const float* Kinv, const float* freqs, __half* ctx, int64_t ld, int B, int res, int D,
                 int pad_cols, cudaStream_t st);
-int person_gather(const float* z32, const float* Kinv, const float* freqs, const float* cq_x,
-                  const float* cq_y, const float* cv_x, const float* cv_y, const int* det_b,
-                  const int* det_y, const int* det_x, const int* count, int max_persons, int res, int D,
-                  float* zc, float* query, float* vals, int ldq, cudaStream_t st);
+int person_gather(const float* z32, const float* xr, const float* norm_g, const float* norm_b, const float* Kinv,
+                  const float* freqs, const float* cq_x, const float* cq_y, const float* cv_x, const float* cv_y,
+                  const int* det_b, const int* det_y, const int* det_x, const int* count, int max_persons, int res,
+                  int D, float* zc, float* query, float* vals, int ldq, cudaStream_t st);
+// central-stream refinement (engine.cu:refine_streams): row indices, input patches and pos-embed rows of the
+// detected cells
+int refine_prepare(const float* img, int S, const float* rowadd, int D, const int* det_b, const int* det_y,
+                   const int* det_x, const int* count, int max_persons, int res, int* rowidx, float* patch,
+                   int ldp, float* xr, cudaStream_t st);
 int kv_add_rows(float* KV, int64_t ldkv, const float* dKV, int ncols, const int* det_b, const int* det_y,
                 const int* det_x, const int* count, int max_persons, int res, cudaStream_t st);
 int skinny_linear(const float* x, int ldx, const int* count, int max_persons, int K, const float* W, int ldw,
                   const float* bias, int Nout, const float* ln_g, const float* ln_b, float ln_eps, int act,
                   const float* resid, int ldr, float* out, int ldo, cudaStream_t st);
+// extras of the skinny linear: fp16 gathered input rows, LayerScale, columns per CTA (0 = pick for occupancy)
+struct SkinnyExtra {
+  const __half* x16 = nullptr;
+  int64_t ldx16 = 0;
+  const int* rowidx = nullptr;
+  const float* gamma = nullptr;
+  int cols = 0;
+};
+int skinny_linear_ex(const float* x, int ldx, const SkinnyExtra& ex, const int* count, int max_persons, int K,
+                     const float* W, int ldw, const float* bias, int Nout, const float* ln_g, const float* ln_b,
+                     float ln_eps, int act, const float* resid, int ldr, float* out, int ldo, cudaStream_t st);
 int hph_self_attn(const float* qkv, int ld, const int* det_b, const int* img_off, const int* count,
                   int max_persons, int heads, float* out, int ldo, cudaStream_t st);
 int hph_cross_attn(const float* q, int ldq, const float* KV, int64_t ldkv, int k_col, int v_col,

@@ -513,11 +513,10 @@ int smplx_forward(const SmplxDeviceModel& bm, const float* rotvec, const float* 
                                                 count, bm.num_betas, bm.center_idx, KT, ws.cf, ws.Amat,
                                                 ws.xf, ws.jposed);
   MHMR_CUDA_CHECK(cudaGetLastError());
-  static bool attr_set = false;
+  static PerDeviceOnce once;
   const int vsmem = static_cast<int>(sizeof(VertSmem)) + 128;
-  if (!attr_set) {
+  if (once.first()) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(smplx_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vsmem));
-    attr_set = true;
   }
   const int tiles = (bm.V + kTV - 1) / kTV;
   smplx_vertex_kernel<<<tiles, kVertThreads, vsmem, st>>>(bm.tmPDX, KT, bm.vt, bm.lbs_weights_padded, ws.cf, ws.Amat,

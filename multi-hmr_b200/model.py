@@ -28,12 +28,23 @@ NUM_VERTS = 10475
 KINEMATIC_JOINTS = ["pelvis", "left_hip", "right_hip", "spine1", "left_knee", "right_knee", "spine2",
                     "left_ankle", "right_ankle", "spine3", "left_foot", "right_foot", "neck", "left_collar",
                     "right_collar", "head", "left_shoulder", "right_shoulder", "left_elbow", "right_elbow",
-                    "left_wrist", "right_wrist", "jaw", "left_eye_smplhf", "right_eye_smplhf"]
+                    "left_wrist", "right_wrist", "jaw", "left_eye_smplhf", "right_eye_smplhf",
+                    "left_index1", "left_index2", "left_index3", "left_middle1", "left_middle2", "left_middle3",
+                    "left_pinky1", "left_pinky2", "left_pinky3", "left_ring1", "left_ring2", "left_ring3",
+                    "left_thumb1", "left_thumb2", "left_thumb3",
+                    "right_index1", "right_index2", "right_index3", "right_middle1", "right_middle2",
+                    "right_middle3", "right_pinky1", "right_pinky2", "right_pinky3", "right_ring1", "right_ring2",
+                    "right_ring3", "right_thumb1", "right_thumb2", "right_thumb3"]
+assert len(KINEMATIC_JOINTS) == 55
+# the 72 non-kinematic names of JOINT_NAMES[:127] (vertex-picked joints and face landmarks): valid in the
+# reference (utils/humans.py:25-26), not supported as a person centre here
+DEFAULT_PERSONS_PER_IMAGE = 16
 
 
 class _Config(ctypes.Structure):
     _fields_ = [(n, c_int) for n in ("arch", "img_size", "max_batch", "max_persons", "xat_depth",
-                                     "xat_num_heads", "num_betas", "person_center_idx", "num_verts")]
+                                     "xat_num_heads", "num_betas", "person_center_idx", "num_verts",
+                                     "refine_central")]
 
 
 _OUT_FIELDS = ("scores_map", "count", "det_idx", "det_score", "offset", "loc", "dist_pp", "dist", "rotmat",
@@ -69,7 +80,7 @@ class Model:
                  camera_embedding="geometric", camera_embedding_num_bands=16,
                  camera_embedding_max_resolution=64, nearness=True, xat_depth=2, xat_num_heads=8,
                  dict_smpl_layer=None, person_center="head", clip_dist=True, num_betas=10, *args,
-                 max_batch=8, max_persons=64, body_model=None, device=None, **kwargs):
+                 max_batch=8, max_persons=None, body_model=None, device=None, refine_central=True, **kwargs):
         if backbone not in ARCH_ID:
             raise ValueError(f"unknown backbone {backbone!r}")
         assert img_size % PATCH_SIZE == 0, "Invalid img size"                      # model.py:65
@@ -81,7 +92,8 @@ class Model:
             raise NotImplementedError("only nearness=True (log-depth) checkpoints are supported")
         assert num_betas in (10, 11)                                                 # model.py:384
         if person_center not in KINEMATIC_JOINTS:
-            raise ValueError(f"person_center {person_center!r} is not a kinematic SMPL-X joint")
+            raise NotImplementedError(f"person_center {person_center!r}: only the 55 kinematic SMPL-X joints are "
+                                      "supported as person centre (vertex-picked joints / landmarks are not)")
         if not torch.cuda.is_available():
             raise RuntimeError("multihmr_b200.Model needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda:0")
@@ -94,7 +106,11 @@ class Model:
         self.xat_depth, self.xat_num_heads, self.num_betas = xat_depth, xat_num_heads, num_betas
         self.person_center = person_center
         self.fovn = 60
-        self.max_batch, self.max_persons = int(max_batch), int(max_persons)
+        # capacity of the per-person buffers for the WHOLE batch; the reference has no limit, so the default
+        # scales with the batch (crowded scenes: 16 persons per image on average)
+        self.max_batch = int(max_batch)
+        self.max_persons = int(max_persons) if max_persons is not None else DEFAULT_PERSONS_PER_IMAGE * self.max_batch
+        self.refine_central = bool(refine_central)
         self.res = img_size // PATCH_SIZE
         self.num_verts = NUM_VERTS
         self._lib = _lib.load()
@@ -159,10 +175,13 @@ class Model:
             return self
         if not hasattr(self, "_bm"):
             raise RuntimeError("no body model: call set_body_model() (SMPL-X buffers) before the first forward")
-        torch.cuda.set_device(self.device)
+        with torch.cuda.device(self.device):
+            return self._finalize_on_device()
+
+    def _finalize_on_device(self):
         cfg = _Config(ARCH_ID[self.backbone_name], self.img_size, self.max_batch, self.max_persons, self.xat_depth,
                       self.xat_num_heads, self.num_betas, KINEMATIC_JOINTS.index(self.person_center),
-                      self.num_verts)
+                      self.num_verts, 1 if self.refine_central else 0)
         h = c_void_p()
         check(self._lib.mhmr_create(ctypes.byref(cfg), ctypes.byref(h)), "mhmr_create")
         self._handle = h
@@ -218,6 +237,10 @@ class Model:
     def forward_raw(self, x, K, idx=None, det_thresh=0.3, nms_kernel_size=3, want_v2d=False, want_z=False):
         """Enqueues one forward and returns (outputs dict of max_persons-sized device tensors, P)."""
         self.finalize()
+        with torch.cuda.device(self.device):
+            return self._forward_raw(x, K, idx, det_thresh, nms_kernel_size, want_v2d, want_z)
+
+    def _forward_raw(self, x, K, idx, det_thresh, nms_kernel_size, want_v2d, want_z):
         if isinstance(det_thresh, list):
             det_thresh = det_thresh[0]                                               # model.py:614-615
         x = x.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
@@ -227,20 +250,42 @@ class Model:
         assert K.shape == (B, 3, 3), "K must be [B,3,3]"
         t = self._alloc_outputs(B, want_v2d, want_z)
         o = _Outputs(*[ptr(t[n]).value if t[n] is not None else None for n in _OUT_FIELDS])
-        fidx, fP = None, 0
+        fidx, fP, unsort = None, 0, None
         if idx is not None:
             fidx = torch.stack([i.to(torch.int64) for i in idx[:4]] if len(idx) >= 4 else
                                [i.to(torch.int64) for i in idx[:3]] + [torch.zeros_like(idx[0], dtype=torch.int64)])
-            fidx = fidx.to(self.device).contiguous()
             fP = int(fidx.shape[1])
+            # the reference indexes tensors with idx and raises IndexError when it is out of range
+            # (model.py:246-255); the kernels trust the indices, so they are validated here
+            h_idx = fidx.cpu()
+            if fP > 0:
+                if (h_idx[0].min() < 0 or h_idx[0].max() >= B or h_idx[1:3].min() < 0
+                        or h_idx[1:3].max() >= self.res):
+                    raise IndexError(f"idx out of range for batch {B} and a {self.res}x{self.res} token grid")
+                if fP > self.max_persons:
+                    raise _lib.MhmrError(f"{fP} forced persons > max_persons {self.max_persons}")
+                if (h_idx[0][1:] < h_idx[0][:-1]).any():
+                    # persons of one image must be contiguous for the engine: run in image order, restore after
+                    order = torch.argsort(h_idx[0], stable=True)
+                    h_idx = h_idx[:, order]
+                    unsort = torch.argsort(order).to(self.device)
+            fidx = h_idx.to(self.device).contiguous()
         stream = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         check(self._lib.mhmr_forward(self._handle, ptr(x), ptr(K), c_int(B), ctypes.c_float(float(det_thresh)),
                                      c_int(int(nms_kernel_size)), ptr(fidx), c_int(fP), ctypes.byref(o), stream),
               "mhmr_forward")
         n = c_int(0)
         check(self._lib.mhmr_sync_count(self._handle, stream, ctypes.byref(n)), "mhmr_sync_count")
+        P = int(n.value)
+        if unsort is not None and P > 0:
+            per_person = ("det_score", "offset", "loc", "dist_pp", "dist", "rotmat", "rotvec", "shape", "expression",
+                          "transl", "transl_pelvis", "v3d", "v2d", "j3d", "j2d")
+            for k in per_person:
+                if t[k] is not None:
+                    t[k][:P] = t[k][:P].index_select(0, unsort)
+            t["det_idx"][:, :P] = t["det_idx"][:, :P].index_select(1, unsort)
         self.last_outputs = t
-        return t, int(n.value)
+        return t, P
 
     def forward(self, x, idx=None, det_thresh=0.3, nms_kernel_size=3, K=None, is_training=False, *args, **kwargs):
         """reference model.py:205-349."""
@@ -278,8 +323,9 @@ class Model:
         x = x.to(self.device, dtype=torch.float32).contiguous()
         B = x.shape[0]
         z = torch.empty(B, self.res * self.res, self.embed_dim, device=self.device)
-        stream = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        check(self._lib.mhmr_vit_forward(self._handle, ptr(x), c_int(B), ptr(z), stream), "mhmr_vit_forward")
+        with torch.cuda.device(self.device):
+            stream = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            check(self._lib.mhmr_vit_forward(self._handle, ptr(x), c_int(B), ptr(z), stream), "mhmr_vit_forward")
         return z
 
     def smplx(self, rotvec, shape, loc, dist, K, expression, want_v2d=True):
@@ -292,11 +338,12 @@ class Model:
         f = lambda *s: torch.empty(*s, device=dev)
         out = {"v3d": f(P, V, 3), "v2d": f(P, V, 2) if want_v2d else None, "j3d": f(P, 127, 3), "j2d": f(P, 127, 2),
                "transl": f(P, 3), "transl_pelvis": f(P, 3)}
-        stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        check(self._lib.mhmr_smplx_forward(self._handle, c_int(P), ptr(rotvec), ptr(shape), ptr(expression), ptr(loc),
-                                           ptr(dist), ptr(K), ptr(out["v3d"]), ptr(out["v2d"]), ptr(out["j3d"]),
-                                           ptr(out["j2d"]), ptr(out["transl"]), ptr(out["transl_pelvis"]), stream),
-              "mhmr_smplx_forward")
+        with torch.cuda.device(dev):
+            stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            check(self._lib.mhmr_smplx_forward(self._handle, c_int(P), ptr(rotvec), ptr(shape), ptr(expression),
+                                               ptr(loc), ptr(dist), ptr(K), ptr(out["v3d"]), ptr(out["v2d"]),
+                                               ptr(out["j3d"]), ptr(out["j2d"]), ptr(out["transl"]),
+                                               ptr(out["transl_pelvis"]), stream), "mhmr_smplx_forward")
         out["transl_pelvis"] = out["transl_pelvis"][:, None]
         return out
 
@@ -304,7 +351,7 @@ class Model:
         return int(self._lib.mhmr_last_launch_count(self._handle))
 
     PROFILE_CATEGORIES = ("misc", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2",
-                          "gemm_other", "head", "smplx")
+                          "gemm_other", "head", "smplx", "refine")
 
     def set_profiling(self, enable: bool):
         self.finalize()

@@ -16,12 +16,10 @@ CASES = {
     "s_448_B_forced": dict(backbone="dinov2_vitb14", img_size=448, batch=2, persons=[3, 1], seed=3, jitter=True),
     "s_224_S_asymK": dict(backbone="dinov2_vits14", img_size=224, batch=2, persons=[2, 2], seed=4, jitter=True,
                           asymmetric=True),
-    # ViT-L depth (24 layers of fp16 tensor-core operands) with the synthetic body model's large extent
-    # (|v3d| up to 4.3 m): measured max |dv3d| = 1.07e-3 = 2.5e-4 relative, every other output <= 7e-4 -- the
-    # fp16 single-pass floor, as for 1288_L in test_fullsize_gpu.py; tolerance 1.5e-3 for this case, documented
-    # in DESIGN.md §3
-    "s_280_L_forced": dict(backbone="dinov2_vitl14", img_size=280, batch=2, persons=[2, 1], seed=5, jitter=True,
-                           tol_scale=1.5),
+    # ViT-L depth (24 layers) with the synthetic body model's large extent (|v3d| up to 4.3 m): the bulk fp16
+    # pass alone gives max |dv3d| = 1.07e-3 here; with the fp32 refinement of the detected tokens' residual
+    # streams it is ~2e-4, inside the 1e-3 contract like every other case
+    "s_280_L_forced": dict(backbone="dinov2_vitl14", img_size=280, batch=2, persons=[2, 1], seed=5, jitter=True),
 }
 
 # Absolute tolerances vs the fp32 reference (BASELINE.json north_star: 1e-3 abs on scores / SMPL-X
@@ -55,11 +53,11 @@ def build_inputs(name):
     return case, sd, bm, x, K, idx
 
 
-def build_engine(case, sd, bm, max_batch=None, max_persons=64):
+def build_engine(case, sd, bm, max_batch=None, max_persons=64, **kw):
     from multihmr_b200.model import Model
 
     m = Model(backbone=case["backbone"], img_size=case["img_size"], num_betas=10,
-              max_batch=max_batch or case["batch"], max_persons=max_persons, body_model=bm)
+              max_batch=max_batch or case["batch"], max_persons=max_persons, body_model=bm, **kw)
     m.load_state_dict(sd, strict=False)
     return m
 
@@ -76,8 +74,9 @@ def _rotvec_to_rotmat(rv):
     return roma_ref.rotvec_to_rotmat(rv)
 
 
-def compare(got: dict, ref: dict, keys, focal=None, verbose=False, tol_scale=1.0):
-    """Returns list of (key, err, tol) that fail; prints a table when verbose."""
+def compare(got: dict, ref: dict, keys, focal=None, verbose=False):
+    """Returns list of (key, err, tol) that fail; prints a table when verbose.  Tolerances are the fixed
+    contract of TOL (1e-3 abs on scores / SMPL-X parameters / 3-D outputs): there is no per-case scaling."""
     bad = []
     for k in keys:
         g, r = got[k].detach().float().cpu(), ref[k].float()
@@ -94,9 +93,7 @@ def compare(got: dict, ref: dict, keys, focal=None, verbose=False, tol_scale=1.0
         tol = TOL.get(k, 1e-3)
         if tol is None:
             src = ref["j3d"] if k == "j2d" else ref["v3d"]
-            tol = projection_tolerance(src, focal, tol3d=1e-3 * tol_scale)
-        else:
-            tol = tol * tol_scale
+            tol = projection_tolerance(src, focal, tol3d=1e-3)
         if verbose:
             print(f"  {k:20s} max|ref|={r.abs().max().item() if r.numel() else 0:10.4f} err={err:.3e} tol={tol:.1e}"
                   f" {'OK' if err <= tol else 'FAIL'}")

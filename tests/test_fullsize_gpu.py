@@ -21,15 +21,15 @@ def _oracle_on_gpu(sd, bm, cfg_kw, x, K, idx, dev):
     return {k: v.float().cpu() for k, v in out.items()}
 
 
-# max-abs tolerance on the metric outputs: 1e-3 (north_star) at the benchmark size; at 1288x1288 (8465
-# tokens x 24 layers) the single-pass fp16 tensor-core arithmetic sits exactly at that level (measured max
-# 1.03e-3 on one of 628k vertex coordinates, mean per-vertex error 0.3 mm), so the stress case allows 1.5e-3
-# max-abs and still requires PVE < 1 mm.
-@pytest.mark.parametrize("name,backbone,S,B,persons,tol3d", [
-    ("896_L", "dinov2_vitl14", 896, 2, [2, 3], 1e-3),
-    ("1288_L_20ppl", "dinov2_vitl14", 1288, 1, [20], 1.5e-3),
+# BASELINE.json configs at their stated sizes: c2 = multiHMR_672_L batch 4, c3 = multiHMR_896_L batch 8,
+# c5 = multiHMR_1288_L batch 2 with 20 persons per image.  One tolerance for all: 1e-3 max-abs on scores,
+# SMPL-X parameters and 3-D vertices (north_star), PVE < 1 mm.
+@pytest.mark.parametrize("name,backbone,S,B,persons", [
+    ("c2_672_L_b4", "dinov2_vitl14", 672, 4, [2, 1, 3, 2]),
+    ("c3_896_L_b8", "dinov2_vitl14", 896, 8, [2, 3, 1, 2, 0, 1, 2, 3]),
+    ("c5_1288_L_b2_20ppl", "dinov2_vitl14", 1288, 2, [20, 20]),
 ])
-def test_engine_vs_oracle_full_size(cuda_device, name, backbone, S, B, persons, tol3d):
+def test_engine_vs_oracle_full_size(cuda_device, name, backbone, S, B, persons):
     from multihmr_b200 import synth
 
     seed = 21
@@ -39,11 +39,11 @@ def test_engine_vs_oracle_full_size(cuda_device, name, backbone, S, B, persons, 
     idx = synth.make_forced_idx(B, S // 14, persons, seed)
     ref = _oracle_on_gpu(sd, bm, dict(backbone=backbone, img_size=S), x, K, idx, cuda_device)
     torch.cuda.empty_cache()
-    m = pu.build_engine(dict(backbone=backbone, img_size=S, batch=B), sd, bm, max_persons=32)
+    m = pu.build_engine(dict(backbone=backbone, img_size=S, batch=B), sd, bm, max_persons=64)
     out = m(x, idx=idx, K=K, is_training=True)
     keys = ["scores", "offset", "dist", "expression", "rotmat", "shape", "rotvec", "loc", "v3d", "j3d", "j2d", "v2d",
             "transl", "transl_pelvis", "dist_postprocessed"]
-    bad = pu.compare(out, ref, keys, focal=float(K[:, 0, 0].max()), verbose=True, tol_scale=tol3d / 1e-3)
+    bad = pu.compare(out, ref, keys, focal=float(K[:, 0, 0].max()), verbose=True)
     # PVE (train.py:387): mean per-vertex error in mm
     pve = (out["v3d"].cpu() - ref["v3d"]).norm(dim=-1).mean().item() * 1000
     print(f"{name}: PVE vs oracle = {pve:.4f} mm over {sum(persons)} persons")
