@@ -131,6 +131,12 @@ int mhmr_finalize(mhmr_engine* h);
 int mhmr_forward(mhmr_engine* h, const float* x, const float* K, int B, float det_thresh,
                  int nms_kernel_size, const int64_t* forced_idx, int forced_P, const mhmr_outputs* out,
                  void* stream);
+/* The same forward fed by the fused image loader (replaces `normalize_rgb` of
+ * utils/image.py:12-24 + the fp32 upload of demo.py:48-50): img_u8 [B,S,S,3] uint8 RGB (HWC, what PIL yields after
+ * ImageOps.pad) and the [3][256] fp32 table of normalize_rgb; uint8 -> normalised fp16 patch rows in one kernel. */
+int mhmr_forward_u8(mhmr_engine* h, const uint8_t* img_u8, const float* lut, const float* K, int B, float det_thresh,
+                    int nms_kernel_size, const int64_t* forced_idx, int forced_P, const mhmr_outputs* out,
+                    void* stream);
 /* Waits for the forward enqueued last on `stream` and returns the person count; MHMR_ERR_CAPACITY if it
  * exceeded max_persons (outputs are then incomplete — never silently truncated). */
 int mhmr_sync_count(mhmr_engine* h, void* stream, int* num_persons);
@@ -164,6 +170,25 @@ int mhmr_comm_create(const void* id128, int world, int rank, mhmr_comm** out);  
 int mhmr_comm_destroy(mhmr_comm* c);
 /* ONE ncclAllGather of the per-rank blocks (all_blocks = world x block_bytes, rank order) on `stream`. */
 int mhmr_allgather_records(mhmr_comm* c, const void* block, void* all_blocks, int64_t block_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation metrics: what the reference's `Trainer.evaluate` (train.py:336-482) computes
+ * from the outputs of Model.forward.  All pointers are DEVICE pointers; nothing synchronises with the host.
+ * ---------------------------------------------------------------------------------------------- */
+/* Replaces utils/training.py:25-147 `match_2d_greedy(pred_kps, gtkp, valid_mask)` (valid=None, as train.py:364
+ * calls it) including the IoU gate of :149-193: pred_j2d [P,J,2], gt_j2d [G,J,2] pixels, valid_mask [G,J] bytes or
+ * NULL (all valid).  Outputs: pairs [min(P,G),2] = (pred, gt) in the order the greedy loop finds them, n_pairs [1],
+ * pred_to_gt [P] (-1 = false positive), gt_to_pred [G] (-1 = miss).  P, G <= 48. */
+int mhmr_eval_match_2d(const float* pred_j2d, const float* gt_j2d, const uint8_t* valid_mask, int P, int G, int J,
+                       float iou_thresh, int32_t* pairs, int32_t* n_pairs, int32_t* pred_to_gt, int32_t* gt_to_pred,
+                       void* stream);
+/* Replaces train.py:373-394 (PVE / PA-PVE) and :411-427 (MPJPE / PA-MPJPE) for the matched pairs: point sets
+ * pred [*,n,3], gt [*,n,3] (metres), optional per-person centres [*,3] subtracted first (the pelvis, train.py:376-382);
+ * err_mm[m] = mean |gt - pred| * 1000, pa_err_mm[m] = the same after the similarity alignment of pred onto gt
+ * (roma.rigid_points_registration(compute_scaling=True)).  One CTA per pair m < *n_pairs (m < max_pairs). */
+int mhmr_eval_points_error(const float* pred, const float* pred_center, const float* gt, const float* gt_center,
+                           const int32_t* pairs, const int32_t* n_pairs, int max_pairs, int n_points, float* err_mm,
+                           float* pa_err_mm, void* stream);
 
 /* Kernel launches enqueued by the last mhmr_forward (bench.py's `gpu_launches`). */
 int mhmr_last_launch_count(mhmr_engine* h);

@@ -14,28 +14,10 @@ import torch
 
 from .model import Model
 
-IMG_NORM_MEAN = [0.485, 0.456, 0.406]       # utils/image.py:8
-IMG_NORM_STD = [0.229, 0.224, 0.225]        # utils/image.py:9
+from .preprocess import IMG_NORM_MEAN, IMG_NORM_STD, device_table, normalize_rgb, normalize_rgb_table  # noqa: F401
+
 SMPLX_DIR = "models"                         # utils/constants.py:7
 CACHE_DIR_MULTIHMR = "models/multiHMR"       # utils/constants.py:9
-
-
-def normalize_rgb(img: np.ndarray, imagenet_normalization: bool = True) -> np.ndarray:
-    """uint8 HWC -> float32 CHW (utils/image.py:12-24)."""
-    img = img.astype(np.float32) / 255.0
-    img = np.transpose(img, (2, 0, 1))
-    if imagenet_normalization:
-        img = (img - np.asarray(IMG_NORM_MEAN).reshape(3, 1, 1)) / np.asarray(IMG_NORM_STD).reshape(3, 1, 1)
-    return img.astype(np.float32)
-
-
-def normalize_rgb_table() -> np.ndarray:
-    """[3, 256] fp32: `normalize_rgb` of every uint8 value in every channel (the table of the device kernel)."""
-    ramp = np.repeat(np.arange(256, dtype=np.uint8)[None, :, None], 3, axis=2)
-    return np.ascontiguousarray(normalize_rgb(ramp)[:, 0, :])
-
-
-_LUT_CACHE = {}
 
 
 def normalize_rgb_device(img_u8: torch.Tensor) -> torch.Tensor:
@@ -43,15 +25,14 @@ def normalize_rgb_device(img_u8: torch.Tensor) -> torch.Tensor:
     host (hand-written kernel, `mhmr_op_normalize_u8`); 4x less to upload than the fp32 image."""
     from . import ops
 
-    key = (img_u8.device.type, img_u8.device.index)
-    if key not in _LUT_CACHE:
-        _LUT_CACHE[key] = torch.from_numpy(normalize_rgb_table()).to(img_u8.device)
-    return ops.normalize_u8(img_u8.contiguous(), _LUT_CACHE[key])
+    return ops.normalize_u8(img_u8.contiguous(), device_table(img_u8.device))
 
 
-def open_image(img_path, img_size, device=torch.device("cuda")):
+def open_image(img_path, img_size, device=torch.device("cuda"), fused=False):
     """Open, resize keeping the aspect ratio, zero-pad to a square, normalise (demo.py:27-51).  On a CUDA
-    device the padded uint8 image is uploaded and normalised there (same values, a quarter of the bytes)."""
+    device the padded uint8 image is uploaded and normalised there (same values, a quarter of the bytes).
+    `fused=True` returns the uint8 [1,S,S,3] device tensor itself: `Model.forward` / `forward_model` then run the
+    fused loader (uint8 -> normalised fp16 patch rows, `mhmr_forward_u8`) and the fp32 image never exists."""
     from PIL import Image, ImageOps
 
     img_pil = Image.open(img_path).convert("RGB")
@@ -61,6 +42,8 @@ def open_image(img_path, img_size, device=torch.device("cuda")):
     device = torch.device(device)
     if device.type == "cuda" and img_size % 4 == 0:
         u8 = torch.from_numpy(np.ascontiguousarray(np.asarray(img_pil))).unsqueeze(0).to(device)
+        if fused:
+            return u8, img_pil_full
         return normalize_rgb_device(u8), img_pil_full
     x = torch.from_numpy(normalize_rgb(np.asarray(img_pil))).unsqueeze(0).to(device)
     return x, img_pil_full
@@ -113,7 +96,7 @@ def body_model_from_smplx_npz(path: str, num_betas: int = 10) -> dict:
     }
 
 
-def load_model(model_name, device=torch.device("cuda"), max_batch=8, max_persons=64):
+def load_model(model_name, device=torch.device("cuda"), max_batch=8, max_persons=None):
     """Open a checkpoint, build the engine from its saved arguments, load the weights (demo.py:70-106).
     No download is attempted (this build has no network): a missing file is an error."""
     ckpt_path = os.path.join(CACHE_DIR_MULTIHMR, model_name + ".pt")

@@ -1,25 +1,18 @@
-// Multi-head self-attention of the DINOv2 backbone (head dim 64) on tcgen05 tensor cores.
+// ROUND-1 kernel (one CTA per query-tile pair), kept for A/B timing against the persistent kernel of attn_tc.cu
+// (MHMR_ATTN_V1=1).  Multi-head self-attention of the DINOv2 backbone (head dim 64) on tcgen05 tensor cores.
 //
 // Replaces `softmax(q k^T / 8) v` of dinov2 `Attention.forward` (reached from the reference at
 // blocks/dinov2.py:25).  Flash-style: the T x T score matrix never leaves the SM.
 //
-//   grid  = one PERSISTENT CTA per SM.  Work items = (image, head, pair of 128-row query tiles), assigned
-//           statically (item i -> CTA i mod grid), query pair fastest so that the CTAs running at the same time
-//           share the K/V of few (image, head) pairs in L2; the ragged last pair of every (image, head) comes
-//           last.  TMEM, barriers and the K/V rings live across items: the next item's Q is prefetched into the
-//           other half of a double-buffered Q area and its first Q K^T is issued while the softmax warps still
-//           finish the previous item, so a CTA pays its prologue and tail once per launch instead of once per
-//           item (r01: 2176 CTAs = 14.7 waves, each with TMEM allocation, barrier init, cold Q/K loads and an
-//           un-overlapped O epilogue: ~18 % of the kernel).
+//   grid  = (ceil(T/256) query-tile pairs, heads, images), one CTA per SM
 //   CTA   = 384 threads = 3 warpgroups: warp 0 TMA, warp 1 MMA issuer (warps 2-3 idle) | warps 4-7 softmax
 //           of query tile 0 | warps 8-11 softmax of query tile 1 (1 thread = 1 query row; setmaxnreg
 //           80 / 208 / 208 registers)
 //   TMEM  = 512 columns: per query tile  S (128 fp32) | P (64 cols = 128 fp16, A operand of P V) | O (64 fp32)
-//   smem  = Q (2 items x 2 tiles x 16 KB) | K ring | V ring (16 KB tiles of 128 keys, 128B swizzle, one TMA each)
+//   smem  = Q (2 x 16 KB) | K ring | V ring (16 KB tiles of 128 keys, 128B swizzle, one TMA each)
 //   S = Q K^T : tcgen05.mma SS, M=128 N=128 K=64     (K tile K-major)
 //   O += P V  : tcgen05.mma TS, M=128 N=64  K=128    (V tile MN-major)
 //   MMA order per key tile j:  S0(j+1) = Q0 K(j+1)^T | O1 += P1(j-1) V(j-1) | S1(j+1) | O0 += P0(j) V(j)
-//   (j+1 of the last key tile of an item = key tile 0 of the CTA's next item)
 // Online softmax in fp32 in the exp2 domain (packed f32x2 FMA/ADD, 3-input max) with lazy rescaling of O
 // (only when the running max grows by more than 2^8), so the O read-modify-write through tcgen05.ld/st is rare.
 //
@@ -37,18 +30,15 @@
 // Issue warps run the whole warp on uniform control flow and elect one lane per issue (elect_one_sync): under
 // `if (lane == 0)` every TMA / MMA / commit costs ~80 clk in an elect-and-retry loop.
 //
-// Barrier phases are tracked with running per-pipeline counters (key tiles fetched, Q K^T / P V issued per
-// query tile, tiles consumed per softmax warp, tokens passed), never with the key-tile index of an item.
-//
 // Ragged sequence (T = N + 1 is 1 mod 128 for every Multi-HMR resolution):
 //   * the last key tile only computes the 16-column groups that hold real keys (QK^T with N = 16..128,
 //     PV with K = 16..128, softmax over the needed 32-column chunks);
 //   * softmax warps whose 32 query rows are all beyond T only keep the barrier protocol alive;
-//   * the last item of an (image, head) holds a single query tile when ceil(T/128) is odd.
+//   * the last CTA of an image holds a single query tile when ceil(T/128) is odd.
 //
 // Diagnostics (never on the product path): MHMR_ATTN_ABLATE=1 (no exponentials) / 4 (protocol only) time the
 // kernel with parts of the softmax removed (wrong results); MHMR_ATTN_ABLATE=7 MHMR_ATTN_TRACE=<file> dumps the
-// SM-clock timeline of the first item of a few CTAs.
+// SM-clock timeline of a few CTAs.
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -66,7 +56,6 @@ constexpr int kBlockKV = 128;
 constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: Q, K or V tile
 constexpr int kBarrierBytes = 512;              // mbarriers + the TMEM slot
 constexpr int kStagesK = 4, kStagesV = 4;
-constexpr int kQTiles = 4;    // two items x two query tiles
 constexpr int kPassAt = 112;  // exponentials issued before the MUFU token is handed on (measured optimum)
 
 constexpr uint32_t kColS = 0;
@@ -83,7 +72,7 @@ __device__ __forceinline__ bool opaque_true() {
 }
 
 // Timeline tracing (MHMR_ATTN_ABLATE=7 MHMR_ATTN_TRACE=file): SM-clock stamps of the protocol events of a few CTAs.
-__device__ uint32_t* g_attn_trace = nullptr;
+__device__ uint32_t* g_attn_trace_v1 = nullptr;
 constexpr int kTraceIters = 40, kTraceEvents = 16, kTraceCtas = 8;
 __device__ __forceinline__ uint32_t clk_after(float dep) {
   uint32_t t;
@@ -95,77 +84,51 @@ constexpr int kAttnThreads = 384;
 constexpr int kRegsIssue = 80, kRegsSoftmax = 208;  // 128 * (80 + 2 * 208) <= 64 K registers
 // Q tiles + K ring + V ring + 1 KB that covers both the 1024-byte alignment of the tiles and the barriers
 // (in front of the tiles when the alignment pad leaves room, behind them otherwise)
-constexpr int attn_smem_bytes(int sk, int sv) { return kTileBytes * (kQTiles + sk + sv) + 1024; }
-
-// Work item -> (image, head, first query row).  Items [0, n_main) are the query-tile pairs qp < n_qp - 1 (query
-// pair fastest); items [n_main, n_items) are the ragged last pairs of every (image, head): cheaper, scheduled last.
-struct AttnItem {
-  int img, head, q0;
-  bool two;
-};
-__device__ __forceinline__ AttnItem attn_decode_item(int idx, int n_qp, int heads, int bh, int T) {
-  AttnItem it;
-  const int n_main = bh * (n_qp - 1);
-  int r, qp;
-  if (idx < n_main) {
-    qp = idx % (n_qp - 1);
-    r = idx / (n_qp - 1);
-  } else {
-    qp = n_qp - 1;
-    r = idx - n_main;
-  }
-  it.head = r % heads;
-  it.img = r / heads;
-  it.q0 = qp * (2 * kBlockQ);
-  it.two = (it.q0 + kBlockQ) < T;
-  return it;
-}
+constexpr int attn_smem_bytes(int sk, int sv) { return kTileBytes * (2 + sk + sv) + 1024; }
 
 template <int kSK, int kSV, int kAb = 0>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
-                int T, int D, int heads, int bh, int n_items, float scale_log2) {
+                 int T, int D, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                                  // [2 items][2 tiles]
-  uint8_t* sK = smem + kTileBytes * kQTiles;           // [kSK]
-  uint8_t* sV = smem + kTileBytes * (kQTiles + kSK);   // [kSV]
+  uint8_t* sQ = smem;                            // [2]
+  uint8_t* sK = smem + kTileBytes * 2;           // [kSK]
+  uint8_t* sV = smem + kTileBytes * (2 + kSK);   // [kSV]
   uint64_t* bars = reinterpret_cast<uint64_t*>((smem - smem_raw) >= kBarrierBytes ? smem_raw
-                                                                                  : smem + kTileBytes * (kQTiles + kSK + kSV));
-  uint64_t* q_full = bars;                 // [2]    TMA -> MMA : Q tiles of an item landed
-  uint64_t* q_empty = bars + 2;            // [2]    MMA -> TMA : every Q K^T of the item that used this half is complete
-  uint64_t* k_full = bars + 4;             // [kSK]  TMA -> MMA
+                                                                                  : smem + kTileBytes * (2 + kSK + kSV));
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // [kSK]  TMA -> MMA
   uint64_t* v_full = k_full + kSK;         // [kSV]  TMA -> MMA
   uint64_t* k_empty = v_full + kSV;        // [kSK]  MMA -> TMA : Q_t K_j^T complete for both query tiles
   uint64_t* v_empty = k_empty + kSK;       // [kSV]  MMA -> TMA : P_t V_j complete for both query tiles
-  uint64_t* s_full = v_empty + kSV;        // [2]    MMA -> softmax t : S_t complete
-  uint64_t* s_empty = s_full + 2;          // [2]    softmax t -> MMA : S_t now in registers
-  uint64_t* p_full = s_empty + 2;          // [2]    softmax t -> MMA : P_t in TMEM (and O_t rescaled / drained)
-  uint64_t* pv_done = p_full + 2;          // [2]    MMA -> softmax t : O_t += P_t V complete
+  uint64_t* s_full = v_empty + kSV;        // [2]    MMA -> softmax t : S_t(j) complete
+  uint64_t* s_empty = s_full + 2;          // [2]    softmax t -> MMA : S_t(j) now in registers
+  uint64_t* p_full = s_empty + 2;          // [2]    softmax t -> MMA : P_t(j) in TMEM (and O_t rescaled)
+  uint64_t* pv_done = p_full + 2;          // [2]    MMA -> softmax t : O_t += P_t(j) V(j) complete
   // MUFU token of each sub-partition.  (Plain shared-memory counters polled with volatile loads were tried
   // instead of mbarriers: the hand-over is quicker, but the polling LDS share the MIO queue with the
   // partner's MUFU.EX2 and the kernel gets 8 % slower.)
-  uint64_t* turn_a = pv_done + 2;          // [4]    tile-0 warp -> tile-1 warp of a sub-partition: exps done
-  uint64_t* turn_b = turn_a + 4;           // [4]    tile-1 warp -> tile-0 warp: exps done
+  uint64_t* turn_a = pv_done + 2;          // [4]    tile-0 warp -> tile-1 warp of a sub-partition: exps(j) done
+  uint64_t* turn_b = turn_a + 4;           // [4]    tile-1 warp -> tile-0 warp: exps(j) done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn_b + 4);
-  static_assert((4 + 2 * kSK + 2 * kSV + 16) * 8 + 4 <= kBarrierBytes, "barrier area too small");
+  static_assert((1 + 2 * kSK + 2 * kSV + 16) * 8 + 4 <= kBarrierBytes, "barrier area too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y, img = blockIdx.z;
+  const int row0 = img * T;              // first token row of this image in the [B*T, 3D] matrix
+  const int q0 = blockIdx.x * (2 * kBlockQ);
+  const bool two = (q0 + kBlockQ < T);   // the last CTA of an image may hold a single query tile
   const int n_kv = (T + kBlockKV - 1) / kBlockKV;
-  const int n_qp = (T + 2 * kBlockQ - 1) / (2 * kBlockQ);
   const int last_valid = T - (n_kv - 1) * kBlockKV;
   const int last_cols = (last_valid + 15) & ~15;
-  const int first_item = blockIdx.x, item_stride = gridDim.x;
 
   griddep_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(&q_full[s], 1);
-        mbar_init(&q_empty[s], 1);
-      }
+      mbar_init(q_full, 1);
       for (int s = 0; s < kSK; ++s) {
         mbar_init(&k_full[s], 1);
         mbar_init(&k_empty[s], 1);
@@ -197,9 +160,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   constexpr bool kTrace = (kAb == 7);
   uint32_t* trace = nullptr;
   if constexpr (kTrace) {
-    const int lin = blockIdx.x;
-    if (g_attn_trace != nullptr && lin >= 3 && (lin - 3) % 17 == 0 && (lin - 3) / 17 < kTraceCtas)
-      trace = g_attn_trace + ((lin - 3) / 17) * kTraceIters * kTraceEvents;
+    const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (g_attn_trace_v1 != nullptr && lin >= 300 && (lin - 300) % 37 == 0 && (lin - 300) / 37 < kTraceCtas)
+      trace = g_attn_trace_v1 + ((lin - 300) / 37) * kTraceIters * kTraceEvents;
   }
   auto stamp = [&](int j, int ev, float dep) {
     if constexpr (kTrace) {
@@ -210,47 +173,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
-    uint32_t kt = 0, it = 0;  // key tiles fetched, items started
-    for (int item = first_item; item < n_items; item += item_stride, ++it) {
-      const AttnItem a = attn_decode_item(item, n_qp, heads, bh, T);
-      const int row0 = a.img * T;  // first token row of this image in the [B*T, 3D] matrix
-      const uint32_t qb = it & 1u;
-      mbar_wait(&q_empty[qb], ((it >> 1) & 1u) ^ 1u);
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(q_full, two ? 2 * kTileBytes : kTileBytes);
+      tma_load_2d(sQ, &tmQKV, q_full, head * kHeadDim, row0 + q0);
+      if (two) tma_load_2d(sQ + kTileBytes, &tmQKV, q_full, head * kHeadDim, row0 + q0 + kBlockQ);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int sk = j % kSK, sv = j % kSV;
+      mbar_wait(&k_empty[sk], ((j / kSK) & 1u) ^ 1u);
       if (elect_one_sync()) {
-        uint8_t* dq = sQ + qb * 2 * kTileBytes;
-        mbar_arrive_expect_tx(&q_full[qb], a.two ? 2 * kTileBytes : kTileBytes);
-        tma_load_2d(dq, &tmQKV, &q_full[qb], a.head * kHeadDim, row0 + a.q0);
-        if (a.two) tma_load_2d(dq + kTileBytes, &tmQKV, &q_full[qb], a.head * kHeadDim, row0 + a.q0 + kBlockQ);
+        mbar_arrive_expect_tx(&k_full[sk], kTileBytes);
+        tma_load_2d(sK + sk * kTileBytes, &tmQKV, &k_full[sk], D + head * kHeadDim, row0 + j * kBlockKV);
       }
-      for (int j = 0; j < n_kv; ++j, ++kt) {
-        const uint32_t sk = kt % kSK, sv = kt % kSV;
-        mbar_wait(&k_empty[sk], ((kt / kSK) & 1u) ^ 1u);
-        if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&k_full[sk], kTileBytes);
-          tma_load_2d(sK + sk * kTileBytes, &tmQKV, &k_full[sk], D + a.head * kHeadDim, row0 + j * kBlockKV);
-        }
-        mbar_wait(&v_empty[sv], ((kt / kSV) & 1u) ^ 1u);
-        if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&v_full[sv], kTileBytes);
-          tma_load_2d(sV + sv * kTileBytes, &tmQKV, &v_full[sv], 2 * D + a.head * kHeadDim, row0 + j * kBlockKV);
-        }
+      mbar_wait(&v_empty[sv], ((j / kSV) & 1u) ^ 1u);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&v_full[sv], kTileBytes);
+        tma_load_2d(sV + sv * kTileBytes, &tmQKV, &v_full[sv], 2 * D + head * kHeadDim, row0 + j * kBlockKV);
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
     constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, false, true);  // B (V) is MN-major
-    uint32_t n_qk[2] = {0u, 0u};  // Q K^T issued on query tile t so far (all items)
-    uint32_t n_pv[2] = {0u, 0u};  // P V issued on query tile t so far
-    // S_t = Q_t K^T for key tile `kt_idx` (ring position) / `j` (index in the item); Q from half `qb`.
-    // `release_k`: last reader of the K stage; `release_q`: last Q K^T of the item on its last tile.
-    auto issue_qk = [&](uint32_t qb, uint32_t kt_idx, int j, int t, bool release_k, bool release_q) {
-      if (n_qk[t] > 0) mbar_wait(&s_empty[t], (n_qk[t] - 1u) & 1u);  // the previous S_t is in registers
-      tc_fence_after();
-      const uint32_t s = kt_idx % kSK;
+    // S_t(j) = Q_t K_j^T; `release_k`: last reader of the K stage
+    auto issue_qk = [&](int j, int t, bool release_k) {
+      const int s = j % kSK;
       const int ncols = (j == n_kv - 1) ? last_cols : kBlockKV;
       const uint32_t idesc_qk = make_idesc_f16(128, ncols, false, false);
-      const uint64_t q_desc = make_sw128_desc(smem_u32(sQ + (qb * 2 + t) * kTileBytes), 16, 1024);
+      const uint64_t q_desc = make_sw128_desc(smem_u32(sQ + t * kTileBytes), 16, 1024);
       const uint64_t k_desc = make_sw128_desc(smem_u32(sK + s * kTileBytes), 16, 1024);
       const uint32_t t_s = tmem_base + t * 256 + kColS;
       if (elect_one_sync()) {
@@ -258,17 +208,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         for (int k = 0; k < kHeadDim / 16; ++k)
           umma_f16_ss(t_s, q_desc + 2u * k, k_desc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
         if (release_k) umma_commit(&k_empty[s]);
-        if (release_q) umma_commit(&q_empty[qb]);
         umma_commit(&s_full[t]);
       }
       __syncwarp();
-      ++n_qk[t];
     };
-    // O_t += P_t V for key tile `kt_idx` / `j`; `release_v`: last reader of the V stage
-    auto issue_pv = [&](uint32_t kt_idx, int j, int t, bool release_v) {
-      mbar_wait(&p_full[t], n_pv[t] & 1u);
-      tc_fence_after();
-      const uint32_t s = kt_idx % kSV;
+    // O_t += P_t(j) V_j; `release_v`: last reader of the V stage
+    auto issue_pv = [&](int j, int t, bool release_v) {
+      const int s = j % kSV;
       // V tile: 128 keys (K) x 64 dims (N), N contiguous: MN-major, 8-key groups 1024 B apart.
       const uint64_t v_desc = make_sw128_desc(smem_u32(sV + s * kTileBytes), 1024, 1024);
       const uint32_t t_p = tmem_base + t * 256 + kColP;
@@ -281,47 +227,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         umma_commit(&pv_done[t]);
       }
       __syncwarp();
-      ++n_pv[t];
     };
 
-    uint32_t kt = 0, it = 0;
-    int item = first_item;
-    if (item < n_items) {
-      AttnItem cur = attn_decode_item(item, n_qp, heads, bh, T);
-      mbar_wait(&q_full[0], 0);
-      mbar_wait(&k_full[0], 0);
-      issue_qk(0, 0, 0, 0, !cur.two, !cur.two && n_kv == 1);
-      if (cur.two) issue_qk(0, 0, 0, 1, true, n_kv == 1);
-      while (true) {
-        const int next_item = item + item_stride;
-        const bool has_next = next_item < n_items;
-        AttnItem nxt = cur;
-        if (has_next) nxt = attn_decode_item(next_item, n_qp, heads, bh, T);
-        const uint32_t qb = it & 1u;
-        for (int j = 0; j < n_kv; ++j, ++kt) {
-          // the step that follows (item, j): (item, j + 1), or key tile 0 of the CTA's next item
-          const bool in_item = (j + 1 < n_kv);
-          const bool follow = in_item || has_next;
-          const AttnItem& f = in_item ? cur : nxt;
-          const uint32_t fqb = in_item ? qb : (qb ^ 1u);
-          const int fj = in_item ? j + 1 : 0;
-          const bool f_last = (fj == n_kv - 1);
-          if (follow) {
-            if (!in_item) mbar_wait(&q_full[fqb], ((it + 1u) >> 1) & 1u);
-            mbar_wait(&k_full[(kt + 1u) % kSK], ((kt + 1u) / kSK) & 1u);
-            issue_qk(fqb, kt + 1u, fj, 0, !f.two, !f.two && f_last);
-          }
-          if (cur.two && j >= 1) issue_pv(kt - 1u, j - 1, 1, true);
-          if (follow && f.two) issue_qk(fqb, kt + 1u, fj, 1, true, f_last);
-          mbar_wait(&v_full[kt % kSV], (kt / kSV) & 1u);
-          issue_pv(kt, j, 0, !cur.two);
-        }
-        if (cur.two) issue_pv(kt - 1u, n_kv - 1, 1, true);
-        if (!has_next) break;
-        item = next_item;
-        cur = nxt;
-        ++it;
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0, !two);
+    if (two) issue_qk(0, 1, true);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) {
+        mbar_wait(&s_empty[0], j & 1u);  // softmax 0 holds S_0(j) in registers
+        mbar_wait(&k_full[(j + 1) % kSK], ((j + 1) / kSK) & 1u);
+        tc_fence_after();
+        issue_qk(j + 1, 0, !two);
       }
+      if (two && j >= 1) {
+        mbar_wait(&p_full[1], (j - 1) & 1u);
+        tc_fence_after();
+        issue_pv(j - 1, 1, true);
+      }
+      if (two && j + 1 < n_kv) {
+        mbar_wait(&s_empty[1], j & 1u);
+        tc_fence_after();
+        issue_qk(j + 1, 1, true);
+      }
+      mbar_wait(&v_full[j % kSV], (j / kSV) & 1u);
+      mbar_wait(&p_full[0], j & 1u);
+      tc_fence_after();
+      issue_pv(j, 0, !two);
+    }
+    if (two) {
+      mbar_wait(&p_full[1], (n_kv - 1) & 1u);
+      tc_fence_after();
+      issue_pv(n_kv - 1, 1, true);
     }
   } else if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
@@ -331,6 +269,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
     const int t = (warp - 4) >> 2;        // query tile of this warp
     const int sub = warp & 3;             // TMEM sub-partition (lane quarter) = SM sub-partition of this warp
     const int row = sub * 32 + lane;
+    const int qt0 = q0 + t * kBlockQ;
     const uint32_t lane_base = static_cast<uint32_t>(sub * 32) << 16;
     const uint32_t t_s = tmem_base + lane_base + t * 256 + kColS;
     const uint32_t t_p = tmem_base + lane_base + t * 256 + kColP;
@@ -341,66 +280,50 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
     uint64_t* my_pv_done = &pv_done[t];
     uint64_t* turn_wait = (t == 0) ? &turn_b[sub] : &turn_a[sub];
     uint64_t* turn_pass = (t == 0) ? &turn_a[sub] : &turn_b[sub];
-    uint32_t n_t = 0;   // key tiles this warp's query tile has been through (all items): phase of s_full / pv_done
-    uint32_t n_tok = 0; // tokens this warp has passed on (two-tile items only)
-    const int last_nch = (last_cols + 31) >> 5;  // 32-column chunks of the last tile that hold real keys
-    const bool tracer_warp = kTrace && sub == 0 && lane == 0;
-
-    for (int item = first_item, seq = 0; item < n_items; item += item_stride, ++seq) {
-      const AttnItem a = attn_decode_item(item, n_qp, heads, bh, T);
-      if (t == 1 && !a.two) continue;  // no second query tile in this item (the MMA warp issues nothing for it)
-      const bool two = a.two;
-      const int qt0 = a.q0 + t * kBlockQ;
-      const bool warp_has_rows = (qt0 + sub * 32) < T;  // warp-uniform
-      const bool row_valid = (qt0 + row) < T;
-      __half* const dst = out + static_cast<int64_t>(a.img * T + qt0 + row) * ldo + a.head * kHeadDim;
-      const uint32_t nb = n_t;                          // phase base of this item
-      // exps(tile 0) waits for the previous exps(tile 1) (none before the CTA's first); exps(tile 1) waits for
-      // exps(tile 0) of the same key tile
-      auto take_turn = [&]() {
-        if (two) {
-          if (t == 0) {
-            if (n_tok > 0) mbar_wait(turn_wait, (n_tok - 1u) & 1u);
-          } else {
-            mbar_wait(turn_wait, n_tok & 1u);
-          }
+    const bool warp_has_rows = (qt0 + sub * 32) < T;  // warp-uniform
+    // exps(tile 0, j) waits for exps(tile 1, j-1); exps(tile 1, j) waits for exps(tile 0, j)
+    auto take_turn = [&](int j) {
+      if (two) {
+        if (t == 0) {
+          if (j > 0) mbar_wait(turn_wait, (j - 1) & 1u);
+        } else {
+          mbar_wait(turn_wait, j & 1u);
         }
-      };
-      auto pass_turn = [&]() {
-        if (two) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(turn_pass);
-          ++n_tok;
-        }
-      };
-
-      if (!warp_has_rows) {
-        // All 32 rows of this warp are beyond the sequence: their S/P/O lanes hold garbage that is never
-        // stored and never mixes with other rows (the MMAs are row-independent); keep the protocol alive.
-        for (int j = 0; j < n_kv; ++j) {
-          mbar_wait(my_s_full, (nb + j) & 1u);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(my_s_empty);
-          take_turn();
-          pass_turn();
-          // arrive on p_full only once the previous P V of this query tile is over: this warp runs ahead of the
-          // warps that do have rows, and an early arrival would complete THEIR pending phase
-          if (nb + j > 0) mbar_wait(my_pv_done, (nb + j - 1u) & 1u);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(my_p_full);
-        }
-        mbar_wait(my_pv_done, (nb + n_kv - 1u) & 1u);
-        n_t = nb + n_kv;
-        continue;
       }
+    };
+    auto pass_turn = [&](int) {
+      if (two) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(turn_pass);
+      }
+    };
 
+    if (t == 1 && !two) {
+      // no second query tile in this CTA
+    } else if (!warp_has_rows) {
+      // All 32 rows of this warp are beyond the sequence: their S/P/O lanes hold garbage that is never
+      // stored and never mixes with other rows (the MMAs are row-independent); keep the protocol alive.
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(my_s_full, j & 1u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(my_s_empty);
+        take_turn(j);
+        pass_turn(j);
+        // arrive on p_full(j) only once phase j-1 is over (P V(j-1) complete implies it): this warp runs
+        // ahead of the warps that do have rows, and an early arrival would complete THEIR pending phase
+        if (j > 0) mbar_wait(my_pv_done, (j - 1) & 1u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(my_p_full);
+      }
+      mbar_wait(my_pv_done, (n_kv - 1) & 1u);
+    } else {
       float m_used = -INFINITY;  // running max (log2 domain) actually used as the exponent offset
       float l = 0.0f;
-      const bool tracer = tracer_warp && seq == 0;
-      // One key tile.  On entry S_t(j) is complete in TMEM (the wait for it happened at the end of tile j-1 /
-      // at the start of the item).  The exponentials are issued as ONE uninterrupted run of MUFU.EX2 between
-      // take_turn and pass_turn; the scale-and-shift before and the row sum / fp16 packing after run under the
-      // partner warp's run.
+
+      const bool tracer = kTrace && sub == 0 && lane == 0;
+      // One key tile.  On entry S_t(j) is complete in TMEM (the wait for it happened at the end of tile j-1).
+      // The exponentials are issued as ONE uninterrupted run of MUFU.EX2 between take_turn and pass_turn; the
+      // scale-and-shift before and the row sum / fp16 packing after run under the partner warp's run.
       auto softmax_tile = [&](auto nch_c, auto last_c, int j) {
         constexpr int NCH = decltype(nch_c)::value;
         constexpr bool kLast = decltype(last_c)::value;  // static: the key mask costs 2 instructions per score
@@ -445,9 +368,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         for (int c = 0; c < NCH; ++c) {
 #pragma unroll
           for (int k = 0; k < 32; k += 2) {
-            const float2 a2 = __ffma2_rn(make_float2(__uint_as_float(s[c][k]), __uint_as_float(s[c][k + 1])), sc2, nm2);
-            s[c][k] = __float_as_uint(a2.x);
-            s[c][k + 1] = __float_as_uint(a2.y);
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(s[c][k]), __uint_as_float(s[c][k + 1])), sc2, nm2);
+            s[c][k] = __float_as_uint(a.x);
+            s[c][k + 1] = __float_as_uint(a.y);
           }
 #pragma unroll
           for (int k = 0; k < 32; k += 16)  // pin: the arguments exist before the token is requested
@@ -458,7 +381,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         }
         if (tracer) stamp(j, t * 8 + 1, 0.f);
         // (B) this warp's turn on the MUFU pipe of its sub-partition
-        take_turn();
+        take_turn(j);
         if (tracer) stamp(j, t * 8 + 2, 0.f);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -469,12 +392,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
               asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(s[c][k])));
               s[c][k] = __float_as_uint(e);
             }
-            // hand the token on kPassAt exponentials into the run (full tiles; at the end of a short last tile):
-            // the partner needs ~150 clk to wake up, its first exponentials then overlap this warp's last ones
+            // hand the token on kPassAt exponentials into the run (full tiles; at the end of a short last tile)
             if ((NCH == 4 && c * 32 + k + 1 == kPassAt) || (NCH < 4 && c == NCH - 1 && k == 31)) {
-              if (opaque_true()) pass_turn();
+              if (opaque_true()) pass_turn(j);
             }
           }
+          // hand the token on a little before the end of the run: the partner needs ~150 clk to wake up
+          // (its first exponentials then overlap this warp's last sixteen)
         }
         if (tracer) stamp(j, t * 8 + 3, __uint_as_float(s[NCH - 1][31]));
         // (C) row sum and fp16 packing -- in a block of its own, so that it is not woven into the MUFU run
@@ -500,9 +424,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         // S_t(j+1) complete also means P V(j-1) complete (the MMA warp issues it earlier): the P buffer is
         // free and O is stable.  One wait serves both, and tile j+1 starts without waiting.
         if (j + 1 < n_kv) {
-          mbar_wait(my_s_full, (nb + j + 1u) & 1u);
+          mbar_wait(my_s_full, (j + 1) & 1u);
         } else if (j > 0) {
-          mbar_wait(my_pv_done, (nb + j - 1u) & 1u);
+          mbar_wait(my_pv_done, (j - 1) & 1u);
         }
         tc_fence_after();
         if (tracer) stamp(j, t * 8 + 5, 0.f);
@@ -526,8 +450,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         if (tracer) stamp(j, t * 8 + 6, 0.f);
       };
 
-      mbar_wait(my_s_full, nb & 1u);
+      mbar_wait(my_s_full, 0);
       tc_fence_after();
+      const int last_nch = (last_cols + 31) >> 5;  // 32-column chunks of the last tile that hold real keys
       for (int j = 0; j < n_kv - 1; ++j) softmax_tile(std::integral_constant<int, 4>{}, std::false_type{}, j);
       switch (last_nch) {
         case 1: softmax_tile(std::integral_constant<int, 1>{}, std::true_type{}, n_kv - 1); break;
@@ -536,17 +461,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
         default: softmax_tile(std::integral_constant<int, 4>{}, std::true_type{}, n_kv - 1); break;
       }
 
-      // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :].  The first P V of the CTA's next item overwrites
-      // O; it is gated by this warp's next arrival on p_full, which comes after these loads.
-      mbar_wait(my_pv_done, (nb + n_kv - 1u) & 1u);
+      // Epilogue: O / l -> fp16 -> out[img*T + q, head*64 + :]
+      mbar_wait(my_pv_done, (n_kv - 1) & 1u);
       tc_fence_after();
       const float inv_l = 1.0f / l;
+      const int q = qt0 + row;
+      __half* dst = out + static_cast<int64_t>(row0 + q) * ldo + head * kHeadDim;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
         tmem_ld_32x32(t_o + c * 32, o);
         tmem_ld_wait();
-        if (row_valid) {
+        if (q < T) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 pk;
@@ -561,8 +487,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
           }
         }
       }
-      tc_fence_before();
-      n_t = nb + n_kv;
     }
   }
 
@@ -574,15 +498,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   }
 }
 
-int g_attn_ablate = -1;  // MHMR_ATTN_ABLATE: timing / tracing experiments only (see the header)
+int g_attn_ablate_v1 = -1;  // MHMR_ATTN_ABLATE: timing / tracing experiments only (see the header)
 
 struct AttnArgs {
   CUtensorMap tm;
   __half* out;
   int64_t ldo;
-  int T, D, heads, bh, n_items;
+  int T, D;
   float scale_log2;
-  int grid;
+  dim3 grid;
   cudaStream_t stream;
 };
 
@@ -595,7 +519,7 @@ int attn_launch(const AttnArgs& a) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(a.grid);
+  cfg.gridDim = a.grid;
   cfg.blockDim = dim3(kAttnThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = a.stream;
@@ -604,7 +528,7 @@ int attn_launch(const AttnArgs& a) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.tm, a.out, a.ldo, a.T, a.D, a.heads, a.bh, a.n_items, a.scale_log2));
+  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.tm, a.out, a.ldo, a.T, a.D, a.scale_log2));
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }
@@ -613,43 +537,35 @@ int attn_launch(const AttnArgs& a) {
 
 // qkv: [B*T, 3*D] fp16 (row pitch ld_qkv), q|k|v column blocks, head h = columns h*64..h*64+63 of each.
 // out: [B*T, D] fp16 (row pitch ldo).
-int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ldo, int B, int T, int D,
-                      cudaStream_t stream) {
+int attention_forward_v1(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ldo, int B, int T, int D,
+                         cudaStream_t stream) {
   MHMR_REQUIRE(D % kHeadDim == 0, "attention: embed dim must be a multiple of 64");
   MHMR_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0, "attention: row pitches must be multiples of 8");
   MHMR_REQUIRE(B > 0 && T > 0, "attention: empty problem");
-  {  // A/B timing against the round-1 kernel (one CTA per query-tile pair): never set on the product path
-    static int use_v1 = -1;
-    if (use_v1 < 0) use_v1 = (std::getenv("MHMR_ATTN_V1") != nullptr) ? 1 : 0;
-    if (use_v1) return attention_forward_v1(qkv, ld_qkv, out, ldo, B, T, D, stream);
-  }
   AttnArgs a;
   int rc = make_tmap_2d(&a.tm, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<uint64_t>(B) * T,
                         3ull * D, ld_qkv * 2, 128, 64, true);
   if (rc != MHMR_OK) return rc;
-  if (g_attn_ablate < 0) {
+  if (g_attn_ablate_v1 < 0) {
     const char* ab = std::getenv("MHMR_ATTN_ABLATE");
-    g_attn_ablate = (ab != nullptr) ? atoi(ab) : 0;
+    g_attn_ablate_v1 = (ab != nullptr) ? atoi(ab) : 0;
   }
   a.out = out;
   a.ldo = ldo;
   a.T = T;
   a.D = D;
-  a.heads = D / kHeadDim;
-  a.bh = B * a.heads;
-  a.n_items = a.bh * ((T + 2 * kBlockQ - 1) / (2 * kBlockQ));
   a.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-  a.grid = a.n_items < device_sm_count() ? a.n_items : device_sm_count();
+  a.grid = dim3((T + 2 * kBlockQ - 1) / (2 * kBlockQ), D / kHeadDim, B);
   a.stream = stream;
-  if (g_attn_ablate == 1) return attn_launch<1>(a);
-  if (g_attn_ablate == 4) return attn_launch<4>(a);
+  if (g_attn_ablate_v1 == 1) return attn_launch<1>(a);
+  if (g_attn_ablate_v1 == 4) return attn_launch<4>(a);
   const char* trace_path = std::getenv("MHMR_ATTN_TRACE");
-  if (g_attn_ablate == 7 && trace_path != nullptr) {
+  if (g_attn_ablate_v1 == 7 && trace_path != nullptr) {
     uint32_t* d_trace = nullptr;
     const size_t trace_words = static_cast<size_t>(kTraceCtas) * kTraceIters * kTraceEvents;
     MHMR_CUDA_CHECK(cudaMalloc(&d_trace, trace_words * 4));
     MHMR_CUDA_CHECK(cudaMemset(d_trace, 0, trace_words * 4));
-    MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &d_trace, sizeof(d_trace)));
+    MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace_v1, &d_trace, sizeof(d_trace)));
     rc = attn_launch<7>(a);
     if (rc != MHMR_OK) return rc;
     MHMR_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -661,7 +577,7 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
     }
     cudaFree(d_trace);
     d_trace = nullptr;
-    MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &d_trace, sizeof(d_trace)));
+    MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace_v1, &d_trace, sizeof(d_trace)));
     return MHMR_OK;
   }
   return attn_launch<0>(a);

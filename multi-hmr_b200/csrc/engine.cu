@@ -383,6 +383,14 @@ int finalize_body(mhmr_engine* e, cudaStream_t st) {
   return MHMR_OK;
 }
 
+// image of a forward: normalised fp32 NCHW (the reference's Model.forward input) or uint8 NHWC + the [3][256]
+// normalize_rgb table (fused loader)
+struct ImgSrc {
+  const float* f32 = nullptr;
+  const uint8_t* u8 = nullptr;
+  const float* lut = nullptr;
+};
+
 struct ProfScope {
   mhmr_engine* e; int cat; cudaStream_t st; cudaEvent_t a{};
   ProfScope(mhmr_engine* e_, int cat_, cudaStream_t st_) : e(e_), cat(cat_), st(st_) {
@@ -410,9 +418,13 @@ int run_plan(mhmr_engine* e, int cat, GemmPlan& plan, int M, cudaStream_t st) {
   return MHMR_OK;
 }
 
-int vit_forward(mhmr_engine* e, const float* x, int B, float* z_out, cudaStream_t st) {
+int vit_forward(mhmr_engine* e, const ImgSrc& x, int B, float* z_out, cudaStream_t st) {
   const int D = e->D, N = e->N, T = e->T, M = B * T;
-  LAUNCH(MHMR_CAT_MISC, im2col_patch14(x, e->A16, B, e->cfg.img_size, 592, st));
+  if (x.u8 != nullptr) {
+    LAUNCH(MHMR_CAT_MISC, im2col_u8_patch14(x.u8, x.lut, e->A16, B, e->cfg.img_size, 592, st));
+  } else {
+    LAUNCH(MHMR_CAT_MISC, im2col_patch14(x.f32, e->A16, B, e->cfg.img_size, 592, st));
+  }
   LAUNCH(MHMR_CAT_MISC, cls_rows(e->X, e->cls_pos, B, T, D, st));
   TRY(run_plan(e, MHMR_CAT_GEMM_OTHER, e->patch_plan, B * N, st));
   for (int l = 0; l < e->depth; ++l) {
@@ -441,10 +453,10 @@ int vit_forward(mhmr_engine* e, const float* x, int B, float* z_out, cudaStream_
 //   x = patch-embed(pixels) + pos;  per block: x += ls1 * (Wproj . O16[row] + b);  x += ls2 * MLP(LN2(x))
 // where O16[row] is the attention output of the bulk pass for that token (kept per layer).  The final norm is
 // applied by person_gather.  Same arithmetic as dinov2 Block.forward (reached from blocks/dinov2.py:25).
-int refine_streams(mhmr_engine* e, const float* x, const int* det_b, const int* det_y, const int* det_x,
+int refine_streams(mhmr_engine* e, const ImgSrc& x, const int* det_b, const int* det_y, const int* det_x,
                    const int* count, cudaStream_t st) {
   const int D = e->D, Pm = e->cfg.max_persons;
-  LAUNCH(MHMR_CAT_REFINE, refine_prepare(x, e->cfg.img_size, e->rowadd, D, det_b, det_y, det_x, count, Pm, e->res,
+  LAUNCH(MHMR_CAT_REFINE, refine_prepare(x.f32, x.u8, x.lut, e->cfg.img_size, e->rowadd, D, det_b, det_y, det_x, count, Pm, e->res,
                                          e->r_rowidx, e->r_patch, 592, e->r_x, st));
   SkinnyExtra none;
   LAUNCH(MHMR_CAT_REFINE, skinny_linear_ex(e->r_patch, 592, none, count, Pm, 588, e->Wpatch32, 588, nullptr, D, nullptr,
@@ -465,7 +477,7 @@ int refine_streams(mhmr_engine* e, const float* x, const int* det_b, const int* 
   return MHMR_OK;
 }
 
-int head_forward(mhmr_engine* e, const float* x, const float* K, int B, float det_thresh, int nms, const int64_t* forced_idx,
+int head_forward(mhmr_engine* e, const ImgSrc& x, const float* K, int B, float det_thresh, int nms, const int64_t* forced_idx,
                  int forced_P, const mhmr_outputs* o, cudaStream_t st) {
   const int D = e->D, N = e->N, res = e->res, Pm = e->cfg.max_persons, Cq = e->Cq, nb = e->cfg.num_betas;
   const int heads = e->cfg.xat_num_heads, inner = heads * 32, BN = B * N;
@@ -616,10 +628,10 @@ int mhmr_finalize(mhmr_engine* h) {
   return MHMR_OK;
 }
 
-int mhmr_forward(mhmr_engine* h, const float* x, const float* K, int B, float det_thresh,
-                 int nms_kernel_size, const int64_t* forced_idx, int forced_P, const mhmr_outputs* out,
-                 void* stream) {
-  MHMR_REQUIRE(h != nullptr && x != nullptr && K != nullptr && out != nullptr, "null argument");
+static int forward_impl(mhmr_engine* h, const ImgSrc& x, const float* K, int B, float det_thresh,
+                        int nms_kernel_size, const int64_t* forced_idx, int forced_P, const mhmr_outputs* out,
+                        void* stream) {
+  MHMR_REQUIRE(h != nullptr && K != nullptr && out != nullptr, "null argument");
   if (!h->finalized) { set_last_error("mhmr_forward before mhmr_finalize"); return MHMR_ERR_STATE; }
   MHMR_REQUIRE(B >= 1 && B <= h->cfg.max_batch, "batch exceeds max_batch");
   MHMR_REQUIRE(forced_idx == nullptr || (forced_P >= 0 && forced_P <= h->cfg.max_persons),
@@ -632,6 +644,25 @@ int mhmr_forward(mhmr_engine* h, const float* x, const float* K, int B, float de
   h->launches = 0;
   TRY(vit_forward(h, x, B, out->z, st));
   return head_forward(h, x, K, B, det_thresh, nms_kernel_size, forced_idx, forced_P, out, st);
+}
+
+int mhmr_forward(mhmr_engine* h, const float* x, const float* K, int B, float det_thresh,
+                 int nms_kernel_size, const int64_t* forced_idx, int forced_P, const mhmr_outputs* out,
+                 void* stream) {
+  MHMR_REQUIRE(x != nullptr, "null image");
+  ImgSrc src;
+  src.f32 = x;
+  return forward_impl(h, src, K, B, det_thresh, nms_kernel_size, forced_idx, forced_P, out, stream);
+}
+
+int mhmr_forward_u8(mhmr_engine* h, const uint8_t* img_u8, const float* lut, const float* K, int B, float det_thresh,
+                    int nms_kernel_size, const int64_t* forced_idx, int forced_P, const mhmr_outputs* out,
+                    void* stream) {
+  MHMR_REQUIRE(img_u8 != nullptr && lut != nullptr, "null image / table");
+  ImgSrc src;
+  src.u8 = img_u8;
+  src.lut = lut;
+  return forward_impl(h, src, K, B, det_thresh, nms_kernel_size, forced_idx, forced_P, out, stream);
 }
 
 int mhmr_sync_count(mhmr_engine* h, void* stream, int* num_persons) {
@@ -651,7 +682,9 @@ int mhmr_vit_forward(mhmr_engine* h, const float* x, int B, float* z, void* stre
   if (!h->finalized) { set_last_error("mhmr_vit_forward before mhmr_finalize"); return MHMR_ERR_STATE; }
   MHMR_REQUIRE(B >= 1 && B <= h->cfg.max_batch, "batch exceeds max_batch");
   h->launches = 0;
-  return vit_forward(h, x, B, z, static_cast<cudaStream_t>(stream));
+  ImgSrc src;
+  src.f32 = x;
+  return vit_forward(h, src, B, z, static_cast<cudaStream_t>(stream));
 }
 
 int mhmr_smplx_forward(mhmr_engine* h, int P, const float* rotvec, const float* shape,

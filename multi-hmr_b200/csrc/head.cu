@@ -277,7 +277,8 @@ person_gather_kernel(const float* __restrict__ z32, const float* __restrict__ xr
 // token matrices (cls row skipped), its 14x14x3 input patch in the order of the patch-embed weight
 // (c, ky, kx: dinov2 PatchEmbed Conv2d) and the fp32 (pos_embed + bias) row of its cell.
 __global__ void __launch_bounds__(256)
-refine_prepare_kernel(const float* __restrict__ img, int S, const float* __restrict__ rowadd, int D,
+refine_prepare_kernel(const float* __restrict__ img, const uint8_t* __restrict__ img_u8,
+                      const float* __restrict__ lut, int S, const float* __restrict__ rowadd, int D,
                       const int* __restrict__ det_b, const int* __restrict__ det_y,
                       const int* __restrict__ det_x, const int* __restrict__ count, int res,
                       int* __restrict__ rowidx, float* __restrict__ patch, int ldp, float* __restrict__ xr) {
@@ -286,12 +287,14 @@ refine_prepare_kernel(const float* __restrict__ img, int S, const float* __restr
   const int b = det_b[p], y = det_y[p], x = det_x[p];
   const int N = res * res, n = y * res + x;
   if (threadIdx.x == 0) rowidx[p] = b * (N + 1) + 1 + n;
-  const float* im = img + static_cast<int64_t>(b) * 3 * S * S;
   for (int k = threadIdx.x; k < ldp; k += 256) {
     float v = 0.f;
     if (k < 588) {
       const int c = k / 196, r = k - c * 196, ky = r / 14, kx = r - ky * 14;
-      v = im[(static_cast<int64_t>(c) * S + y * 14 + ky) * S + x * 14 + kx];
+      if (img_u8 != nullptr)  // fused uint8 loader: the fp32 pixel is the table entry (normalize_rgb, bit-exact)
+        v = lut[c * 256 + img_u8[((static_cast<int64_t>(b) * S + y * 14 + ky) * S + x * 14 + kx) * 3 + c]];
+      else
+        v = img[((static_cast<int64_t>(b) * 3 + c) * S + y * 14 + ky) * S + x * 14 + kx];
     }
     patch[static_cast<int64_t>(p) * ldp + k] = v;
   }
@@ -681,11 +684,12 @@ int person_gather(const float* z32, const float* xr, const float* norm_g, const 
   return MHMR_OK;
 }
 
-int refine_prepare(const float* img, int S, const float* rowadd, int D, const int* det_b, const int* det_y,
-                   const int* det_x, const int* count, int max_persons, int res, int* rowidx, float* patch,
-                   int ldp, float* xr, cudaStream_t st) {
+int refine_prepare(const float* img, const uint8_t* img_u8, const float* lut, int S, const float* rowadd, int D,
+                   const int* det_b, const int* det_y, const int* det_x, const int* count, int max_persons, int res,
+                   int* rowidx, float* patch, int ldp, float* xr, cudaStream_t st) {
   MHMR_REQUIRE(ldp >= 588 && ldp % 4 == 0, "refine_prepare: patch pitch must be >= 588 and a multiple of 4");
-  refine_prepare_kernel<<<max_persons, 256, 0, st>>>(img, S, rowadd, D, det_b, det_y, det_x, count, res, rowidx,
+  MHMR_REQUIRE((img != nullptr) != (img_u8 != nullptr), "refine_prepare: exactly one image source");
+  refine_prepare_kernel<<<max_persons, 256, 0, st>>>(img, img_u8, lut, S, rowadd, D, det_b, det_y, det_x, count, res, rowidx,
                                                      patch, ldp, xr);
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;

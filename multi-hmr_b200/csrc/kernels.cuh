@@ -7,10 +7,13 @@ namespace mhmr {
 // ---- attn_tc.cu ------------------------------------------------------------------------------
 int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ldo, int B, int T, int D,
                       cudaStream_t stream);
+int attention_forward_v1(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ldo, int B, int T, int D,
+                         cudaStream_t stream);  // attn_tc_v1.cu: round-1 kernel, A/B timing only
 
 // ---- vit_misc.cu -----------------------------------------------------------------------------
 int im2col_patch14(const float* x, __half* A, int B, int S, int ldA, cudaStream_t stream);
 int normalize_u8(const uint8_t* img, const float* lut, float* out, int B, int H, int W, cudaStream_t stream);
+int im2col_u8_patch14(const uint8_t* img, const float* lut, __half* A, int B, int S, int ldA, cudaStream_t stream);
 int cls_rows(float* X, const float* cls_pos, int B, int T, int D, cudaStream_t stream);
 int layernorm(const float* X, const float* gamma, const float* beta, __half* out16, int64_t ld16,
               float* out32, int64_t ld32, int M, int D, float eps, int rows_in, int skip,
@@ -41,7 +44,7 @@ int person_gather(const float* z32, const float* xr, const float* norm_g, const 
                   int D, float* zc, float* query, float* vals, int ldq, cudaStream_t st);
 // central-stream refinement (engine.cu:refine_streams): row indices, input patches and pos-embed rows of the
 // detected cells
-int refine_prepare(const float* img, int S, const float* rowadd, int D, const int* det_b, const int* det_y,
+int refine_prepare(const float* img, const uint8_t* img_u8, const float* lut, int S, const float* rowadd, int D, const int* det_b, const int* det_y,
                    const int* det_x, const int* count, int max_persons, int res, int* rowidx, float* patch,
                    int ldp, float* xr, cudaStream_t st);
 int kv_add_rows(float* KV, int64_t ldkv, const float* dKV, int ncols, const int* det_b, const int* det_y,

@@ -243,9 +243,14 @@ class Model:
     def _forward_raw(self, x, K, idx, det_thresh, nms_kernel_size, want_v2d, want_z):
         if isinstance(det_thresh, list):
             det_thresh = det_thresh[0]                                               # model.py:614-615
-        x = x.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        fused = x.dtype == torch.uint8   # uint8 [B,S,S,3] RGB: fused loader (normalize_rgb + patch rows in one kernel)
+        if fused:
+            x = x.to(self.device, non_blocking=True).contiguous()
+            assert x.dim() == 4 and x.shape[3] == 3 and x.shape[1] == x.shape[2] == self.img_size, "bad image shape"
+        else:
+            x = x.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            assert x.dim() == 4 and x.shape[1] == 3 and x.shape[2] == x.shape[3] == self.img_size, "bad image shape"
         K = K.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
-        assert x.dim() == 4 and x.shape[1] == 3 and x.shape[2] == x.shape[3] == self.img_size, "bad image shape"
         B = x.shape[0]
         assert K.shape == (B, 3, 3), "K must be [B,3,3]"
         t = self._alloc_outputs(B, want_v2d, want_z)
@@ -271,9 +276,16 @@ class Model:
                     unsort = torch.argsort(order).to(self.device)
             fidx = h_idx.to(self.device).contiguous()
         stream = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        check(self._lib.mhmr_forward(self._handle, ptr(x), ptr(K), c_int(B), ctypes.c_float(float(det_thresh)),
-                                     c_int(int(nms_kernel_size)), ptr(fidx), c_int(fP), ctypes.byref(o), stream),
-              "mhmr_forward")
+        if fused:
+            from .preprocess import device_table
+            lut = device_table(self.device)
+            check(self._lib.mhmr_forward_u8(self._handle, ptr(x), ptr(lut), ptr(K), c_int(B),
+                                            ctypes.c_float(float(det_thresh)), c_int(int(nms_kernel_size)), ptr(fidx),
+                                            c_int(fP), ctypes.byref(o), stream), "mhmr_forward_u8")
+        else:
+            check(self._lib.mhmr_forward(self._handle, ptr(x), ptr(K), c_int(B), ctypes.c_float(float(det_thresh)),
+                                         c_int(int(nms_kernel_size)), ptr(fidx), c_int(fP), ctypes.byref(o), stream),
+                  "mhmr_forward")
         n = c_int(0)
         check(self._lib.mhmr_sync_count(self._handle, stream, ctypes.byref(n)), "mhmr_sync_count")
         P = int(n.value)

@@ -132,6 +132,33 @@ def make_state_dict(backbone: str = "dinov2_vitl14", img_size: int = 896, num_be
     return sd
 
 
+def add_outlier_channels(sd: dict, backbone: str, seed: int = 0, magnitude: float = 60.0) -> dict:
+    """DINOv2-like 'massive activations' on top of make_state_dict (in place; the random stream of make_state_dict
+    is untouched, so the other fixtures do not change): a few residual channels carry values of O(100) — on a few
+    tokens from the position embedding on, and on every token after two MLP blocks whose fc2 rows / LayerScale for
+    those channels are large.  Trained ViTs have such channels; N(0, 0.02) weights alone do not, and fp16
+    tensor-core operands (Xn16 / QKV16 / H16) are stressed differently by them."""
+    cfg = BACKBONES[backbone]
+    D, depth = cfg["embed_dim"], cfg["depth"]
+    g = _gen(seed + 909)
+    ch = torch.randperm(D, generator=g)[:4]
+    e = "backbone.encoder."
+    pos = sd[e + "pos_embed"].clone()
+    cells = 1 + torch.randperm(37 * 37, generator=g)[:40]          # ~3 % of the pretraining grid
+    for c in ch[:2]:
+        pos[0, cells, c] += magnitude * (0.5 + torch.rand(cells.numel(), generator=g))
+    sd[e + "pos_embed"] = pos
+    for l in (depth // 3, depth // 2):
+        b = f"{e}blocks.{l}."
+        w = sd[b + "mlp.fc2.weight"].clone()
+        w[ch[2:]] *= 25.0
+        sd[b + "mlp.fc2.weight"] = w
+        gma = sd[b + "ls2.gamma"].clone()
+        gma[ch[2:]] = 1.0
+        sd[b + "ls2.gamma"] = gma
+    return sd
+
+
 def make_mean_params(seed: int = 0) -> dict:
     """pose[144] (24 joints x 6D, in the (a1, a2) order rot6d_to_rotmat reads, utils/humans.py:20),
     shape[10], cam[3]."""
@@ -181,6 +208,12 @@ def make_images(batch: int, img_size: int, seed: int = 0) -> torch.Tensor:
     """fp32 NCHW in the range normalize_rgb produces (utils/image.py:8-24)."""
     g = _gen(seed + 303)
     return torch.randn(batch, 3, img_size, img_size, generator=g).clamp_(-2.1, 2.6)
+
+
+def make_images_u8(batch: int, img_size: int, seed: int = 0) -> torch.Tensor:
+    """uint8 [B,S,S,3] RGB (HWC), what PIL + ImageOps.pad yield in demo.py:33-47 before normalize_rgb."""
+    g = _gen(seed + 313)
+    return torch.randint(0, 256, (batch, img_size, img_size, 3), generator=g, dtype=torch.uint8)
 
 
 def make_cameras(batch: int, img_size: int, fov_deg=60.0, jitter: bool = False, seed: int = 0,

@@ -40,6 +40,9 @@ CASES = {
     # the ViT-L architecture (depth 24, 16 heads, D = 1024) of the headline configs, at a size the CPU reference
     # runs in seconds; rectangular per-image intrinsics
     "s_280_L_forced": dict(backbone="dinov2_vitl14", img_size=280, batch=2, persons=[2, 1], seed=5, jitter=True),
+    # DINOv2-like massive-activation channels (synth.add_outlier_channels): residual values of O(100)
+    "s_224_S_outliers": dict(backbone="dinov2_vits14", img_size=224, batch=2, persons=[2, 1], seed=6, jitter=True,
+                             outliers=True),
 }
 
 _CURRENT_BM = {}
@@ -102,6 +105,8 @@ def run_case(name, case, out_dir):
     torch.set_num_threads(os.cpu_count())
     seed = case["seed"]
     sd = synth.make_state_dict(case["backbone"], case["img_size"], seed=seed, det_bias=case.get("det_bias", -4.0))
+    if case.get("outliers"):
+        synth.add_outlier_channels(sd, case["backbone"], seed)
     bm = synth.make_body_model(seed)
     mean = synth.make_mean_params(seed)
     x = synth.make_images(case["batch"], case["img_size"], seed)
@@ -167,6 +172,63 @@ def run_normalize_rgb(out_dir):
     print(f"normalize_rgb: table {table.shape} {table.dtype}, restatement bit-exact")
 
 
+def make_matching_cases():
+    """Seeded 2-D keypoint sets (pixels) for the matching golden: persons are blobs of 127 joints; predictions are
+    noisy copies of some ground truths plus spurious far-away ones (false positives) and missing ones (misses)."""
+    rng = np.random.default_rng(123)
+    cases = []
+    for (G, keep, extra) in [(1, 1, 0), (3, 3, 0), (4, 2, 1), (2, 2, 3), (5, 4, 2), (3, 0, 2), (2, 0, 0), (6, 6, 1)]:
+        centers = rng.uniform(100, 800, size=(G, 1, 2))
+        gt = centers + rng.normal(0, 40, size=(G, 127, 2))
+        order = rng.permutation(G)[:keep]
+        preds = [gt[g] + rng.normal(0, 6, size=(127, 2)) for g in order]
+        for _ in range(extra):
+            c = rng.uniform(2000, 3000, size=(1, 2)) if rng.random() < 0.5 else centers[rng.integers(G)] + rng.normal(0, 60, size=(1, 2))
+            preds.append(c + rng.normal(0, 40, size=(127, 2)))
+        perm = rng.permutation(len(preds)) if preds else []
+        pred = np.stack([preds[i] for i in perm]) if len(preds) else np.zeros((0, 127, 2))
+        cases.append((pred.astype(np.float32), gt.astype(np.float32)))
+    return cases
+
+
+def run_eval_matching(out_dir):
+    """Golden of the evaluation helpers: the reference's OWN match_2d_greedy / get_bbx_overlap /
+    compute_prf1 (utils/training.py, loaded as a file: it only needs numpy + torch) on seeded keypoint sets; the
+    restatement oracle/eval_ref.py must agree exactly."""
+    import importlib.util
+
+    from oracle import eval_ref
+
+    spec = importlib.util.spec_from_file_location("_ref_utils_training", os.path.join(REFERENCE, "utils", "training.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = {}
+    for i, (pred, gt) in enumerate(make_matching_cases()):
+        vm = np.ones_like(gt[..., 0]).astype(np.bool_)
+        if len(pred):
+            best, fps, misses = mod.match_2d_greedy(pred, gt, vm)
+        else:  # train.py:363 builds an empty array when nothing is detected: every ground truth is a miss
+            best, fps, misses = np.zeros((0, 2), dtype=np.int64), [], list(range(len(gt)))
+        best = np.asarray(best, dtype=np.int64).reshape(-1, 2)
+        mine = eval_ref.match_2d_greedy(pred, gt, vm)
+        assert np.array_equal(mine[0], best) and list(mine[1]) == [int(v) for v in fps] and list(mine[2]) == [int(v) for v in misses], i
+        ious = np.array([[mod.get_bbx_overlap(p, g) for g in gt] for p in pred]).reshape(len(pred), len(gt))
+        mine_iou = np.array([[eval_ref.get_bbx_overlap(p, g) for g in gt] for p in pred]).reshape(len(pred), len(gt))
+        assert np.allclose(ious, mine_iou, rtol=0, atol=0)
+        gold[f"pred{i}"], gold[f"gt{i}"], gold[f"best{i}"] = pred, gt, best
+        gold[f"fp{i}"], gold[f"miss{i}"] = np.asarray(fps, dtype=np.int64), np.asarray(misses, dtype=np.int64)
+        gold[f"iou{i}"] = ious.astype(np.float64)
+    prf = []
+    for (c, m, f) in [(0, 0, 0), (10, 2, 1), (7, 7, 3), (25, 0, 0), (13, 5, 9)]:
+        r = mod.compute_prf1(c, m, f)
+        assert tuple(r) == tuple(eval_ref.compute_prf1(c, m, f))
+        prf.append([c, m, f, *r])
+    gold["prf1"] = np.asarray(prf, dtype=np.float64)
+    gold["n_cases"] = np.asarray(len(make_matching_cases()))
+    np.savez_compressed(os.path.join(out_dir, "eval_matching.npz"), **gold)
+    print(f"eval_matching: {int(gold['n_cases'])} cases, restatement == reference (matches, false positives, misses, IoU, PRF1)")
+
+
 def main():
     assert os.path.isdir(REFERENCE), "make_golden needs the reference checkout (build container only)"
     install_shims()
@@ -175,6 +237,8 @@ def main():
     only = sys.argv[1:]
     if not only or "normalize_rgb" in only:
         run_normalize_rgb(out_dir)
+    if not only or "eval_matching" in only:
+        run_eval_matching(out_dir)
     for name, case in CASES.items():
         if only and name not in only:
             continue

@@ -84,3 +84,29 @@ def unitquat_to_rotvec(quat: torch.Tensor) -> torch.Tensor:
 
 def rotmat_to_rotvec(R: torch.Tensor) -> torch.Tensor:
     return unitquat_to_rotvec(rotmat_to_unitquat(R))
+
+
+def special_procrustes(M: torch.Tensor):
+    """roma.special_procrustes(M, return_singular_values=True): the rotation closest to M (Frobenius), through the
+    SVD with the reflection fix on the last singular direction.  Returns (R, signed singular values)."""
+    U, D, Vh = torch.linalg.svd(M)
+    det = torch.det(U) * torch.det(Vh)
+    sign = torch.ones_like(D)
+    sign[..., -1] = det
+    R = (U * sign[..., None, :]) @ Vh
+    return R, D * sign
+
+
+def rigid_points_registration(x: torch.Tensor, y: torch.Tensor, compute_scaling: bool = False):
+    """roma.rigid_points_registration (utils/rigid_points_registration of naver/roma; call sites train.py:391,424):
+    the similarity (R, t, s) minimising sum ||s R x_i + t - y_i||^2 (Kabsch / Umeyama).  x, y: [..., n, 3]."""
+    xmean, ymean = x.mean(dim=-2, keepdim=True), y.mean(dim=-2, keepdim=True)
+    xhat, yhat = x - xmean, y - ymean
+    M = torch.einsum("...ki,...kj->...ij", yhat, xhat)
+    R, DS = special_procrustes(M)
+    if compute_scaling:
+        scale = DS.sum(dim=-1) / (xhat**2).sum(dim=(-1, -2))
+        t = ymean.squeeze(-2) - scale[..., None] * (R @ xmean.squeeze(-2)[..., None]).squeeze(-1)
+        return R, t, scale
+    t = ymean.squeeze(-2) - (R @ xmean.squeeze(-2)[..., None]).squeeze(-1)
+    return R, t

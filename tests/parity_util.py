@@ -20,6 +20,9 @@ CASES = {
     # pass alone gives max |dv3d| = 1.07e-3 here; with the fp32 refinement of the detected tokens' residual
     # streams it is ~2e-4, inside the 1e-3 contract like every other case
     "s_280_L_forced": dict(backbone="dinov2_vitl14", img_size=280, batch=2, persons=[2, 1], seed=5, jitter=True),
+    # DINOv2-like massive-activation channels (synth.add_outlier_channels): residual values of O(100)
+    "s_224_S_outliers": dict(backbone="dinov2_vits14", img_size=224, batch=2, persons=[2, 1], seed=6, jitter=True,
+                             outliers=True),
 }
 
 # Absolute tolerances vs the fp32 reference (BASELINE.json north_star: 1e-3 abs on scores / SMPL-X
@@ -43,6 +46,8 @@ def build_inputs(name):
     case = CASES[name]
     seed = case["seed"]
     sd = synth.make_state_dict(case["backbone"], case["img_size"], seed=seed, det_bias=case.get("det_bias", -4.0))
+    if case.get("outliers"):
+        synth.add_outlier_channels(sd, case["backbone"], seed)
     bm = synth.make_body_model(seed)
     x = synth.make_images(case["batch"], case["img_size"], seed)
     K = synth.make_cameras(case["batch"], case["img_size"], jitter=case.get("jitter", False), seed=seed,

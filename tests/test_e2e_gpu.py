@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["s_224_S_forced", "s_448_B_forced", "c1_672_S_forced", "s_224_S_asymK",
-                                  "s_280_L_forced"])
+                                  "s_280_L_forced", "s_224_S_outliers"])
 def test_forced_idx_matches_reference(cuda_device, name):
     case, sd, bm, x, K, idx = pu.build_inputs(name)
     gold = pu.load_golden(name)

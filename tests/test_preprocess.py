@@ -73,3 +73,22 @@ def test_open_image_device_path_equals_host_path(cuda_device, tmp_path):
     x_dev, _ = api.open_image(path, 224, device=cuda_device)
     x_host, _ = api.open_image(path, 224, device=torch.device("cpu"))
     assert x_dev.is_cuda and torch.equal(x_dev.cpu(), x_host)
+
+
+@pytest.mark.gpu
+def test_fused_uint8_loader_equals_normalize_then_forward(cuda_device):
+    """Model.forward on the uint8 HWC image (fused loader: uint8 -> normalised fp16 patch rows in
+    one kernel, mhmr_forward_u8) gives bit-identical outputs to Model.forward on normalize_rgb(image) — with and
+    without the fp32 refinement of the detected tokens (which re-reads the pixels of its patches)."""
+    import parity_util as pu
+    from multihmr_b200 import api, synth
+
+    case, sd, bm, _, K, idx = pu.build_inputs("s_224_S_forced")
+    u8 = synth.make_images_u8(case["batch"], case["img_size"], seed=3)
+    x32 = torch.from_numpy(np.stack([api.normalize_rgb(im.numpy()) for im in u8]))
+    for refine in (True, False):
+        m = pu.build_engine(case, sd, bm, refine_central=refine)
+        a = {k: v.clone() for k, v in m(x32, idx=idx, K=K, is_training=True).items()}
+        b = m(u8.to(cuda_device), idx=idx, K=K, is_training=True)
+        for k in ("scores", "v3d", "rotmat", "shape", "dist", "loc", "j2d", "offset"):
+            assert torch.equal(a[k], b[k]), (refine, k)

@@ -1,0 +1,13 @@
+#!/bin/bash
+# staged GPU run: new attention kernel first (falls back to the round-1 kernel for the rest if it fails)
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_attention_gpu.py -q -x > gpurun_out/r02b_attn.log 2>&1
+if [ $? -ne 0 ]; then echo "NEW ATTENTION FAILED -> MHMR_ATTN_V1" >> gpurun_out/r02b_attn.log; export MHMR_ATTN_V1=1; fi
+tail -3 gpurun_out/r02b_attn.log
+timeout 600 python tools/bench_ops.py --what attention --out gpurun_out/r02b_attn_new.json > gpurun_out/r02b_ops.log 2>&1
+MHMR_ATTN_V1=1 timeout 600 python tools/bench_ops.py --what attention --out gpurun_out/r02b_attn_v1.json >> gpurun_out/r02b_ops.log 2>&1
+cat gpurun_out/r02b_ops.log | grep attention
+timeout 1800 python -m pytest tests -m gpu -q -s --deselect tests/test_attention_gpu.py > gpurun_out/r02b_pytest.log 2>&1
+grep -n "passed\|failed" gpurun_out/r02b_pytest.log | tail -3
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02b_bench.json 2> gpurun_out/r02b_bench.err
+cat gpurun_out/r02b_bench.json
