@@ -188,7 +188,9 @@ class OursBench:
         self.B, self.S = B, S
         self.max_persons = max(64, 2 * B * w["target_persons_per_image"])
         # ---- setup (untimed): weights, calibration of the synthetic detection density, final engine
-        self.x_host = synth.make_images(B, S, seed=w["seed"] + rank).pin_memory()
+        # uint8 RGB HWC, what open_image produces before normalize_rgb (demo.py:33-47): the engine's fused loader
+        # normalises on the device, so a step uploads 3 bytes per pixel instead of 12
+        self.x_host = synth.make_images_u8(B, S, seed=w["seed"] + rank).pin_memory()
         self.K_host = synth.make_cameras(B, S, seed=w["seed"] + rank).pin_memory()
         sd = synth.make_state_dict(w["backbone"], S, seed=w["seed"], det_bias=0.0)
         bm = synth.make_body_model(w["seed"])
@@ -324,7 +326,7 @@ def run_ours(args):
     ms_e2e, last, _ = bench.timed(bench.step_e2e, args.steps, max(1, args.warmup // 2))
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     P_e2e, d2h_bytes = last
-    h2d_bytes = bench.x_host.numel() * 4 + bench.K_host.numel() * 4
+    h2d_bytes = bench.x_host.numel() * bench.x_host.element_size() + bench.K_host.numel() * 4
 
     # ---- per-kernel-family breakdown (separate pass, events around every launch)
     prof_steps = max(1, min(args.steps, 5))
@@ -401,6 +403,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "fp16 tensor-core operands, fp32 accumulate/residual",
         "data": "synthetic",
         "config": {"workload": f"{w['name']} batch {B}/GPU, synthetic {S}x{S}, random-init ViT-L weights",
+                   "input": "uint8 RGB HWC images (fused normalize_rgb + patch-row loader on the device)",
                    "images_per_gpu": B, "global_batch": world * B, "persons_in_batch": int(P_last),
                    "det_thresh": w["det_thresh"], "nms_kernel_size": w["nms_kernel_size"],
                    "parallelism": f"dp{world} (image shards, 1 all-gather of person records)" if world > 1 else "dp1",

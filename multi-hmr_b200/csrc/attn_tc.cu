@@ -67,6 +67,8 @@ constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: Q, K or V tile
 constexpr int kBarrierBytes = 512;              // mbarriers + the TMEM slot
 constexpr int kStagesK = 4, kStagesV = 4;
 constexpr int kQTiles = 4;    // two items x two query tiles
+constexpr int kDefaultPoly = 0;      // default MHMR_ATTN_POLY level
+constexpr int kDefaultSimtTail = 0;  // default MHMR_ATTN_TAIL (1: ragged tail rows on the idle warps)
 constexpr int kPassAt = 112;  // exponentials issued before the MUFU token is handed on (measured optimum)
 
 constexpr uint32_t kColS = 0;
@@ -91,8 +93,27 @@ __device__ __forceinline__ uint32_t clk_after(float dep) {
   return t;
 }
 
+// exp2 of two exponent arguments on the FMA / ALU pipes (no MUFU): round-to-nearest range reduction with the
+// 1.5 * 2^23 trick, degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (relative error 7.5e-5, below the 4.9e-4 of the
+// fp16 rounding P gets anyway), exponent inserted with an integer shift-add.  10 instructions per pair.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float2 xc = make_float2(fmaxf(x.x, -125.0f), fmaxf(x.y, -125.0f));
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 t = __fadd2_rn(xc, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), xc);
+  float2 p = __ffma2_rn(make_float2(0.0551716685295105f, 0.0551716685295105f), f,
+                        make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
 constexpr int kAttnThreads = 384;
-constexpr int kRegsIssue = 80, kRegsSoftmax = 208;  // 128 * (80 + 2 * 208) <= 64 K registers
+constexpr int kRegsIssue = 88, kRegsSoftmax = 208;  // 128 * (88 + 2 * 208) <= 64 K registers
 // Q tiles + K ring + V ring + 1 KB that covers both the 1024-byte alignment of the tiles and the barriers
 // (in front of the tiles when the alignment pad leaves room, behind them otherwise)
 constexpr int attn_smem_bytes(int sk, int sv) { return kTileBytes * (kQTiles + sk + sv) + 1024; }
@@ -121,10 +142,14 @@ __device__ __forceinline__ AttnItem attn_decode_item(int idx, int n_qp, int head
   return it;
 }
 
-template <int kSK, int kSV, int kAb = 0>
+// kPolyMask: which of the 32 scores of a chunk get their exponential from exp2_poly2 instead of MUFU.EX2 (pairs of
+// adjacent bits).  MUFU.EX2 issues once per 8 clk per sub-partition; the warp that owns the MUFU token has idle issue
+// slots in between, and the polynomial pairs are woven into them: fewer MUFU instructions per key tile.
+template <int kSK, int kSV, int kAb = 0, uint32_t kPolyMask = 0u>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int64_t ldo,
-                int T, int D, int heads, int bh, int n_items, float scale_log2) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restrict__ qkv, int64_t ld_qkv,
+                __half* __restrict__ out, int64_t ldo, int T, int D, int heads, int bh, int n_qp, int n_items,
+                int tail_rows, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                  // [2 items][2 tiles]
@@ -153,7 +178,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_kv = (T + kBlockKV - 1) / kBlockKV;
-  const int n_qp = (T + 2 * kBlockQ - 1) / (2 * kBlockQ);
   const int last_valid = T - (n_kv - 1) * kBlockKV;
   const int last_cols = (last_valid + 15) & ~15;
   const int first_item = blockIdx.x, item_stride = gridDim.x;
@@ -325,6 +349,114 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
     }
   } else if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssue));
+    // ------------------------------ ragged tail rows (SIMT) ---------------------
+    // T = N + 1 leaves T mod 256 query rows (1 for every Multi-HMR resolution but 1288: 17) beyond the full
+    // query-tile pairs.  As a work item of the tensor-core path such a row costs almost a full item (one softmax
+    // warp works alone, 127 of 128 MMA rows are padding): 128 items = 5 % of the kernel at 896 / batch 8.  These two
+    // otherwise idle warps compute them instead, concurrently with the items of the CTA: task = (image, head, row),
+    // 8 lanes per key (8 head dims each), 8 keys in flight per iteration, fp32 online softmax in the exp2 domain.
+    if (tail_rows > 0) {
+      __shared__ float tail_scratch[8][12];
+      const int w2 = warp - 2, grp = lane >> 3, sub8 = lane & 7;
+      const int n_tasks = bh * tail_rows;
+      for (int task = gridDim.x - 1 - blockIdx.x; task < n_tasks; task += gridDim.x) {
+        const int r = task / tail_rows, qrow = n_qp * (2 * kBlockQ) + (task - r * tail_rows);
+        const int head = r % heads, img = r / heads;
+        const __half* base = qkv + static_cast<int64_t>(img) * T * ld_qkv + head * kHeadDim + 8 * sub8;
+        float q[8];
+        {
+          const uint4 pk = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(qrow) * ld_qkv);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h2[i]);
+            q[2 * i] = f.x * scale_log2;
+            q[2 * i + 1] = f.y * scale_log2;
+          }
+        }
+        float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        constexpr int kU = 4;  // keys in flight per lane group
+        for (int k0 = w2 * 4 + grp; k0 < T; k0 += 8 * kU) {
+          uint4 kk[kU], vv[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const int key = k0 + 8 * u;
+            const int64_t off = static_cast<int64_t>(key < T ? key : 0) * ld_qkv;
+            kk[u] = *reinterpret_cast<const uint4*>(base + off + D);
+            vv[u] = *reinterpret_cast<const uint4*>(base + off + 2 * D);
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const __half2* k2 = reinterpret_cast<const __half2*>(&kk[u]);
+            float sdot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(k2[i]);
+              sdot = fmaf(q[2 * i], f.x, sdot);
+              sdot = fmaf(q[2 * i + 1], f.y, sdot);
+            }
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+            if (k0 + 8 * u >= T) sdot = -INFINITY;
+            const float mn = fmaxf(m, sdot);
+            const float a = (mn == -INFINITY) ? 1.f : exp2f(m - mn);
+            const float p = (mn == -INFINITY) ? 0.f : exp2f(sdot - mn);
+            l = l * a + p;
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vv[u]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(v2[i]);
+              acc[2 * i] = fmaf(p, f.x, acc[2 * i] * a);
+              acc[2 * i + 1] = fmaf(p, f.y, acc[2 * i + 1] * a);
+            }
+            m = mn;
+          }
+        }
+        // merge the 4 lane groups of the warp, then the two warps through shared memory
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+          const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+          const float mn = fmaxf(m, m2);
+          const float a = (m == -INFINITY) ? 0.f : exp2f(m - mn);
+          const float b = (m2 == -INFINITY) ? 0.f : exp2f(m2 - mn);
+          l = l * a + l2 * b;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float c2 = __shfl_xor_sync(0xffffffffu, acc[i], o);
+            acc[i] = acc[i] * a + c2 * b;
+          }
+          m = mn;
+        }
+        if (w2 == 1 && lane < 8) {
+          tail_scratch[lane][0] = m;
+          tail_scratch[lane][1] = l;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) tail_scratch[lane][2 + i] = acc[i];
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (w2 == 0 && lane < 8) {
+          const float m2 = tail_scratch[lane][0], l2 = tail_scratch[lane][1];
+          const float mn = fmaxf(m, m2);
+          const float a = (m == -INFINITY) ? 0.f : exp2f(m - mn);
+          const float b = (m2 == -INFINITY) ? 0.f : exp2f(m2 - mn);
+          const float inv = 1.0f / (l * a + l2 * b);
+          uint4 pk;
+          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __half2 h = __floats2half2_rn((acc[2 * i] * a + tail_scratch[lane][2 + 2 * i] * b) * inv,
+                                                (acc[2 * i + 1] * a + tail_scratch[lane][3 + 2 * i] * b) * inv);
+            pw[i] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(img) * T + qrow) * ldo + head * kHeadDim + 8 * sub8) = pk;
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");  // the scratch is free for the next task
+      }
+    }
   } else {
     // ------------------------------ Softmax warps ------------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
@@ -463,16 +595,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ 
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            if constexpr (kAb != 1 && kAb != 4) {
-              float e;
-              asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(s[c][k])));
-              s[c][k] = __float_as_uint(e);
+          for (int h = 0; h < 2; ++h) {
+            // MUFU.EX2 first (they queue up in the MUFU pipe, one per 8 clk), then the polynomial pairs of this
+            // half-chunk on the FMA / ALU pipes while the queue drains
+#pragma unroll
+            for (int k = h * 16; k < h * 16 + 16; ++k) {
+              if constexpr (kAb != 1 && kAb != 4) {
+                if (!((kPolyMask >> k) & 1u)) {
+                  float e;
+                  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(s[c][k])));
+                  s[c][k] = __float_as_uint(e);
+                }
+              }
+              // hand the token on kPassAt exponentials into the run (full tiles; at the end of a short last tile):
+              // the partner needs ~150 clk to wake up, its first exponentials then overlap this warp's last ones
+              if ((NCH == 4 && c * 32 + k + 1 == kPassAt) || (NCH < 4 && c == NCH - 1 && k == 31)) {
+                if (opaque_true()) pass_turn();
+              }
             }
-            // hand the token on kPassAt exponentials into the run (full tiles; at the end of a short last tile):
-            // the partner needs ~150 clk to wake up, its first exponentials then overlap this warp's last ones
-            if ((NCH == 4 && c * 32 + k + 1 == kPassAt) || (NCH < 4 && c == NCH - 1 && k == 31)) {
-              if (opaque_true()) pass_turn();
+            if constexpr (kPolyMask != 0u && kAb != 1 && kAb != 4) {
+#pragma unroll
+              for (int k = h * 16; k < h * 16 + 16; k += 2) {
+                if ((kPolyMask >> k) & 1u) {
+                  const float2 e2 = exp2_poly2(make_float2(__uint_as_float(s[c][k]), __uint_as_float(s[c][k + 1])));
+                  s[c][k] = __float_as_uint(e2.x);
+                  s[c][k + 1] = __float_as_uint(e2.y);
+                }
+              }
+              // scheduling fence: ptxas would otherwise hoist every MUFU of the tile in front of all the
+              // polynomial work (in-order issue would then serialise the two)
+              if (!opaque_true()) return;
             }
           }
         }
@@ -578,18 +730,20 @@ int g_attn_ablate = -1;  // MHMR_ATTN_ABLATE: timing / tracing experiments only 
 
 struct AttnArgs {
   CUtensorMap tm;
+  const __half* qkv;
+  int64_t ld_qkv;
   __half* out;
   int64_t ldo;
-  int T, D, heads, bh, n_items;
+  int T, D, heads, bh, n_qp, n_items, tail_rows;
   float scale_log2;
   int grid;
   cudaStream_t stream;
 };
 
-template <int kAb>
+template <int kAb, uint32_t kPolyMask = 0u>
 int attn_launch(const AttnArgs& a) {
   constexpr int smem = attn_smem_bytes(kStagesK, kStagesV);
-  auto kern = attn_fwd_kernel<kStagesK, kStagesV, kAb>;
+  auto kern = attn_fwd_kernel<kStagesK, kStagesV, kAb, kPolyMask>;
   static PerDeviceOnce once;
   if (once.first()) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -604,7 +758,8 @@ int attn_launch(const AttnArgs& a) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.tm, a.out, a.ldo, a.T, a.D, a.heads, a.bh, a.n_items, a.scale_log2));
+  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.tm, a.qkv, a.ld_qkv, a.out, a.ldo, a.T, a.D, a.heads, a.bh, a.n_qp,
+                                     a.n_items, a.tail_rows, a.scale_log2));
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }
@@ -635,11 +790,23 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   a.ldo = ldo;
   a.T = T;
   a.D = D;
+  a.qkv = qkv;
+  a.ld_qkv = ld_qkv;
   a.heads = D / kHeadDim;
   a.bh = B * a.heads;
-  a.n_items = a.bh * ((T + 2 * kBlockQ - 1) / (2 * kBlockQ));
+  // query rows beyond the full 256-row pairs: few of them (<= 32) go to the SIMT tail warps, more stay a ragged item
+  static int simt_tail = -1;
+  if (simt_tail < 0) {
+    const char* te = std::getenv("MHMR_ATTN_TAIL");
+    simt_tail = (te != nullptr) ? atoi(te) : kDefaultSimtTail;
+  }
+  const int rem = T % (2 * kBlockQ);
+  a.tail_rows = (simt_tail != 0 && rem >= 1 && rem <= 32) ? rem : 0;
+  a.n_qp = (a.tail_rows > 0) ? T / (2 * kBlockQ) : (T + 2 * kBlockQ - 1) / (2 * kBlockQ);
+  a.n_items = a.bh * a.n_qp;
   a.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-  a.grid = a.n_items < device_sm_count() ? a.n_items : device_sm_count();
+  const int work = a.n_items > a.bh * a.tail_rows ? a.n_items : a.bh * a.tail_rows;
+  a.grid = work < device_sm_count() ? work : device_sm_count();
   a.stream = stream;
   if (g_attn_ablate == 1) return attn_launch<1>(a);
   if (g_attn_ablate == 4) return attn_launch<4>(a);
@@ -663,6 +830,17 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
     d_trace = nullptr;
     MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &d_trace, sizeof(d_trace)));
     return MHMR_OK;
+  }
+  static int poly = -1;  // MHMR_ATTN_POLY: share of the exponentials computed on the FMA pipes (experiments)
+  if (poly < 0) {
+    const char* pe = std::getenv("MHMR_ATTN_POLY");
+    poly = (pe != nullptr) ? atoi(pe) : kDefaultPoly;
+  }
+  switch (poly) {
+    case 1: return attn_launch<0, 0xC000C000u>(a);   // 4 of 32
+    case 2: return attn_launch<0, 0xC0C0C0C0u>(a);   // 8 of 32
+    case 3: return attn_launch<0, 0xCC30CC30u>(a);   // 12 of 32
+    default: break;
   }
   return attn_launch<0>(a);
 }

@@ -329,12 +329,24 @@ skinny_linear_kernel(const float* __restrict__ x, int ldx, const __half* __restr
                      const float* __restrict__ gamma, const float* __restrict__ resid, int ldr,
                      float* __restrict__ out, int ldo, int cols) {
   extern __shared__ float xs[];  // [kSkinnyPT][Kp], Kp = K rounded up to 4
+  const int Kp = (K + 3) & ~3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Programmatic dependent launch: the weights do not depend on the preceding kernel, so this CTA's weight rows are
+  // pulled into L2 while that kernel drains; everything it produced (count, activations) is read after the wait.
+  griddep_launch_dependents();
+  if (blockIdx.y == 0) {
+    for (int c = warp; c < cols; c += 8) {
+      const int n = blockIdx.x * cols + c;
+      if (n >= Nout) break;
+      const char* wr = reinterpret_cast<const char*>(W + static_cast<int64_t>(n) * ldw);
+      for (int b = lane * 128; b < Kp * 4; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(wr + b));
+    }
+  }
+  griddep_wait();
   const int P = *count;
   const int p0 = blockIdx.y * kSkinnyPT;
   if (p0 >= P) return;
   const int np = min(kSkinnyPT, P - p0);
-  const int Kp = (K + 3) & ~3;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // stage (and optionally LayerNorm) one person row per warp
   {
@@ -722,10 +734,18 @@ int skinny_linear_ex(const float* x, int ldx, const SkinnyExtra& ex, const int* 
   if (ex.cols <= 0) {
     while (cols > 8 && (Nout + cols - 1) / cols < 2 * device_sm_count()) cols >>= 1;
   }
-  dim3 grid((Nout + cols - 1) / cols, (max_persons + kSkinnyPT - 1) / kSkinnyPT);
-  skinny_linear_kernel<<<grid, 256, smem, st>>>(x, ldx, ex.x16, ex.ldx16, ex.rowidx, count, K, W, ldw, bias, Nout,
-                                                ln_g, ln_b, ln_eps, act, ex.gamma, resid, ldr, out, ldo, cols);
-  MHMR_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((Nout + cols - 1) / cols, (max_persons + kSkinnyPT - 1) / kSkinnyPT);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, skinny_linear_kernel, x, ldx, ex.x16, ex.ldx16, ex.rowidx, count, K, W, ldw,
+                                     bias, Nout, ln_g, ln_b, ln_eps, act, ex.gamma, resid, ldr, out, ldo, cols));
   return MHMR_OK;
 }
 

@@ -6,7 +6,19 @@ if [ $? -ne 0 ]; then echo "NEW ATTENTION FAILED -> MHMR_ATTN_V1" >> gpurun_out/
 tail -3 gpurun_out/r02b_attn.log
 timeout 600 python tools/bench_ops.py --what attention --out gpurun_out/r02b_attn_new.json > gpurun_out/r02b_ops.log 2>&1
 MHMR_ATTN_V1=1 timeout 600 python tools/bench_ops.py --what attention --out gpurun_out/r02b_attn_v1.json >> gpurun_out/r02b_ops.log 2>&1
-cat gpurun_out/r02b_ops.log | grep attention
+for p in 1 2 3; do
+  echo "POLY=$p" >> gpurun_out/r02b_ops.log
+  MHMR_ATTN_POLY=$p timeout 600 python tools/bench_ops.py --what attention --out gpurun_out/r02b_attn_poly$p.json >> gpurun_out/r02b_ops.log 2>&1
+done
+MHMR_ATTN_POLY=2 timeout 900 python -m pytest tests/test_attention_gpu.py -q > gpurun_out/r02b_attn_poly2_test.log 2>&1
+tail -2 gpurun_out/r02b_attn_poly2_test.log
+MHMR_ATTN_TAIL=1 timeout 900 python -m pytest tests/test_attention_gpu.py -q > gpurun_out/r02b_attn_tail_test.log 2>&1
+tail -2 gpurun_out/r02b_attn_tail_test.log
+for p in 0 2; do
+  echo "TAIL=1 POLY=$p" >> gpurun_out/r02b_ops.log
+  MHMR_ATTN_TAIL=1 MHMR_ATTN_POLY=$p timeout 600 python tools/bench_ops.py --what attention --out gpurun_out/r02b_attn_tail_poly$p.json >> gpurun_out/r02b_ops.log 2>&1
+done
+grep 'attention\|POLY\|TAIL' gpurun_out/r02b_ops.log
 timeout 1800 python -m pytest tests -m gpu -q -s --deselect tests/test_attention_gpu.py > gpurun_out/r02b_pytest.log 2>&1
 grep -n "passed\|failed" gpurun_out/r02b_pytest.log | tail -3
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02b_bench.json 2> gpurun_out/r02b_bench.err
