@@ -16,7 +16,7 @@ w = bench.WORKLOAD
 B, S = int(os.environ.get("MHMR_PROF_BATCH", w["batch_per_gpu"])), w["img_size"]
 dev = torch.device("cuda:0")
 sd, bm = bench.build_workload(det_bias=0.0)
-x = synth.make_images(B, S, seed=w["seed"]).to(dev)
+x = synth.make_images_u8(B, S, seed=w["seed"]).to(dev)   # uint8 HWC: the fused loader, as in bench.py
 K = synth.make_cameras(B, S, seed=w["seed"]).to(dev)
 idx = synth.make_forced_idx(B, S // 14, w["target_persons_per_image"], seed=w["seed"])
 m = Model(backbone=w["backbone"], img_size=S, max_batch=B, max_persons=128, body_model=bm, device=dev)
