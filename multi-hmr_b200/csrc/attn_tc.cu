@@ -68,6 +68,7 @@ constexpr int kBarrierBytes = 512;              // mbarriers + the TMEM slot
 constexpr int kStagesK = 4, kStagesV = 4;
 constexpr int kQTiles = 4;    // two items x two query tiles
 constexpr int kDefaultPoly = 0;      // default MHMR_ATTN_POLY level
+constexpr int kDefaultUseV1 = 1;     // 1 until the persistent kernel is validated on hardware (MHMR_ATTN_V1=0 selects it)
 constexpr int kDefaultHelper = 0;    // default MHMR_ATTN_HELPER (1: polynomial-exponential helper warps)
 constexpr int kDefaultSimtTail = 0;  // default MHMR_ATTN_TAIL (1: ragged tail rows on the idle warps)
 constexpr int kPassAt = 112;  // exponentials issued before the MUFU token is handed on (measured optimum)
@@ -898,9 +899,12 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   MHMR_REQUIRE(D % kHeadDim == 0, "attention: embed dim must be a multiple of 64");
   MHMR_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0, "attention: row pitches must be multiples of 8");
   MHMR_REQUIRE(B > 0 && T > 0, "attention: empty problem");
-  {  // A/B timing against the round-1 kernel (one CTA per query-tile pair): never set on the product path
+  {  // A/B against the round-1 kernel (one CTA per query-tile pair); MHMR_ATTN_V1=0 / 1 overrides the default
     static int use_v1 = -1;
-    if (use_v1 < 0) use_v1 = (std::getenv("MHMR_ATTN_V1") != nullptr) ? 1 : 0;
+    if (use_v1 < 0) {
+      const char* ve = std::getenv("MHMR_ATTN_V1");
+      use_v1 = (ve != nullptr) ? atoi(ve) : kDefaultUseV1;
+    }
     if (use_v1) return attention_forward_v1(qkv, ld_qkv, out, ldo, B, T, D, stream);
   }
   AttnArgs a;

@@ -1,6 +1,7 @@
 #!/bin/bash
 # staged GPU run: new attention kernel first (falls back to the round-1 kernel for the rest if it fails)
 mkdir -p gpurun_out
+export MHMR_ATTN_V1=0
 timeout 900 python -m pytest tests/test_attention_gpu.py -q -x > gpurun_out/r02b_attn.log 2>&1
 if [ $? -ne 0 ]; then echo "NEW ATTENTION FAILED -> MHMR_ATTN_V1" >> gpurun_out/r02b_attn.log; export MHMR_ATTN_V1=1; fi
 tail -3 gpurun_out/r02b_attn.log
