@@ -151,6 +151,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int m0 = m_blk * BM2 + static_cast<int>(rank) * 128;
       const int n0 = n_blk * BN2 + static_cast<int>(rank) * (BN2 / 2);
+      if constexpr (EPI == EPI_LS_RESID_F32) {
+        // The epilogue of proj / fc2 reads 128 KB of the fp32 residual stream per tile straight from HBM (written a
+        // whole layer ago) and is latency-bound on it (r01: proj at 44 % DRAM).  The producer warp runs at most the
+        // smem ring ahead of the tensor pipe: when it starts a tile it pulls that tile's residual rows into L2, a
+        // whole main loop before the epilogue asks for them (prefetch.global.L2 is a hint: no hazard with the
+        // in-place update).
+        const int nc0 = n_blk * BN2;
+        const int ncols = min(BN2, N - nc0);
+        for (int r = lane; r < 128; r += 32) {
+          if (m0 + r >= M) break;
+          const char* row = reinterpret_cast<const char*>(reinterpret_cast<const float*>(ep.out) +
+                                                          static_cast<int64_t>(m0 + r) * ep.ldo + nc0);
+          for (int b = 0; b < ncols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+        }
+        __syncwarp();
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = smem + stage * kStageBytes2;

@@ -34,3 +34,12 @@ if grep -q "failed" gpurun_out/r02b_pytest.log; then
 fi
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02b_bench.json 2> gpurun_out/r02b_bench.err
 cat gpurun_out/r02b_bench.json
+
+# ---- second half: fastest validated attention variant -> full test pass, profiles, bench legs
+python tools/pick_attn_variant.py > gpurun_out/r02b_pick.txt 2>&1
+cat gpurun_out/r02b_pick.txt
+eval "$(grep '^export' gpurun_out/r02b_pick.txt)"
+env | grep MHMR_ > gpurun_out/r02b_env.txt
+timeout 1200 python -m pytest tests/test_e2e_gpu.py tests/test_fullsize_gpu.py -q > gpurun_out/r02b_pytest_best.log 2>&1
+grep -n "passed\|failed" gpurun_out/r02b_pytest_best.log | tail -2
+bash tools/gpu_r02c.sh
