@@ -69,6 +69,7 @@ constexpr int kStagesK = 4, kStagesV = 4;
 constexpr int kQTiles = 4;    // two items x two query tiles
 constexpr int kDefaultPoly = 0;      // default MHMR_ATTN_POLY level
 constexpr int kDefaultUseV1 = 1;     // 1 until the persistent kernel is validated on hardware (MHMR_ATTN_V1=0 selects it)
+constexpr int kDefaultToken = 0;     // default MHMR_ATTN_TOKEN (0: mbarrier token)
 constexpr int kDefaultHelper = 0;    // default MHMR_ATTN_HELPER (1: polynomial-exponential helper warps)
 constexpr int kDefaultSimtTail = 0;  // default MHMR_ATTN_TAIL (1: ragged tail rows on the idle warps)
 constexpr int kPassAt = 112;  // exponentials issued before the MUFU token is handed on (measured optimum)
@@ -154,7 +155,10 @@ __device__ __forceinline__ AttnItem attn_decode_item(int idx, int n_qp, int head
 // softmax warps (different warps: the hardware scheduler interleaves them, no ptxas scheduling games).  The softmax
 // warp of a (tile, quarter) still takes the row max over all 128 columns and publishes the exponent offset through
 // shared memory; the helper keeps the partial row sums of its columns and hands them over at the end of an item.
-template <int kSK, int kSV, int kAb = 0, uint32_t kPolyMask = 0u, int kHelp = 0>
+// kTok = 1: the MUFU token travels through named barriers (bar.arrive / bar.sync, ids 2..9) instead of mbarriers:
+// the timeline shows ~340 clk between the mbarrier arrive and the partner's first exponential (the arrive queues behind
+// the MUFU instructions in flight and the waiter wakes up late); kPass = exponentials issued before the hand-over.
+template <int kSK, int kSV, int kAb = 0, uint32_t kPolyMask = 0u, int kHelp = 0, int kTok = 0, int kPass = kPassAt>
 __global__ void __launch_bounds__(kHelp ? kAttnThreadsHelp : kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restrict__ qkv, int64_t ld_qkv,
                 __half* __restrict__ out, int64_t ldo, int T, int D, int heads, int bh, int n_qp, int n_items,
@@ -601,17 +605,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
       // exps(tile 0) of the same key tile
       auto take_turn = [&]() {
         if (two) {
-          if (t == 0) {
-            if (n_tok > 0) mbar_wait(turn_wait, (n_tok - 1u) & 1u);
+          if constexpr (kTok == 1) {
+            if (t == 1 || n_tok > 0) asm volatile("bar.sync %0, 64;" ::"r"(t == 0 ? 6 + sub : 2 + sub) : "memory");
           } else {
-            mbar_wait(turn_wait, n_tok & 1u);
+            if (t == 0) {
+              if (n_tok > 0) mbar_wait(turn_wait, (n_tok - 1u) & 1u);
+            } else {
+              mbar_wait(turn_wait, n_tok & 1u);
+            }
           }
         }
       };
       auto pass_turn = [&]() {
         if (two) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(turn_pass);
+          if constexpr (kTok == 1) {
+            asm volatile("bar.arrive %0, 64;" ::"r"(t == 0 ? 2 + sub : 6 + sub) : "memory");
+          } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(turn_pass);
+          }
           ++n_tok;
         }
       };
@@ -729,7 +741,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
               }
               // hand the token on kPassAt exponentials into the run (full tiles; at the end of a short last tile):
               // the partner needs ~150 clk to wake up, its first exponentials then overlap this warp's last ones
-              if ((NCH == 4 && c * 32 + k + 1 == (kHelp ? kPassAt - kHelpCols : kPassAt)) ||
+              if ((NCH == 4 && c * 32 + k + 1 == (kHelp ? kPass - kHelpCols : kPass)) ||
                   (NCH < 4 && c == NCH - 1 && k == 31)) {
                 if (opaque_true()) pass_turn();
               }
@@ -866,10 +878,10 @@ struct AttnArgs {
   cudaStream_t stream;
 };
 
-template <int kAb, uint32_t kPolyMask = 0u, int kHelp = 0>
+template <int kAb, uint32_t kPolyMask = 0u, int kHelp = 0, int kTok = 0, int kPass = kPassAt>
 int attn_launch(const AttnArgs& a) {
   constexpr int smem = attn_smem_bytes(kStagesK, kStagesV);
-  auto kern = attn_fwd_kernel<kStagesK, kStagesV, kAb, kPolyMask, kHelp>;
+  auto kern = attn_fwd_kernel<kStagesK, kStagesV, kAb, kPolyMask, kHelp, kTok, kPass>;
   static PerDeviceOnce once;
   if (once.first()) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -970,7 +982,14 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
     const char* he = std::getenv("MHMR_ATTN_HELPER");
     helper = (he != nullptr) ? atoi(he) : kDefaultHelper;
   }
-  if (helper != 0) return attn_launch<0, 0u, 1>(a);
+  static int tok = -1;  // MHMR_ATTN_TOKEN: 1 / 2 = named-barrier MUFU token, handed on after 112 / 124 exponentials
+  if (tok < 0) {
+    const char* tk = std::getenv("MHMR_ATTN_TOKEN");
+    tok = (tk != nullptr) ? atoi(tk) : kDefaultToken;
+  }
+  if (helper != 0) return tok ? attn_launch<0, 0u, 1, 1, 120>(a) : attn_launch<0, 0u, 1>(a);
+  if (tok == 1) return attn_launch<0, 0u, 0, 1, 112>(a);
+  if (tok == 2) return attn_launch<0, 0u, 0, 1, 124>(a);
   switch (poly) {
     case 1: return attn_launch<0, 0xC000C000u>(a);   // 4 of 32
     case 2: return attn_launch<0, 0xC0C0C0C0u>(a);   // 8 of 32

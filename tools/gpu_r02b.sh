@@ -21,11 +21,19 @@ for tl in 0 1; do
   echo "HELPER=1 TAIL=$tl" >> gpurun_out/r02b_ops.log
   MHMR_ATTN_HELPER=1 MHMR_ATTN_TAIL=$tl timeout 600 python tools/bench_ops.py --what attention --out gpurun_out/r02b_attn_helper_tail$tl.json >> gpurun_out/r02b_ops.log 2>&1
 done
+MHMR_ATTN_TOKEN=1 timeout 900 python -m pytest tests/test_attention_gpu.py -q > gpurun_out/r02b_attn_token_test.log 2>&1
+tail -2 gpurun_out/r02b_attn_token_test.log
+for tk in 1 2; do
+  echo "TOKEN=$tk TAIL=1" >> gpurun_out/r02b_ops.log
+  MHMR_ATTN_TOKEN=$tk MHMR_ATTN_TAIL=1 timeout 600 python tools/bench_ops.py --what attention --out gpurun_out/r02b_attn_token${tk}_tail1.json >> gpurun_out/r02b_ops.log 2>&1
+done
+echo "TOKEN=1 HELPER=1 TAIL=1" >> gpurun_out/r02b_ops.log
+MHMR_ATTN_TOKEN=1 MHMR_ATTN_HELPER=1 MHMR_ATTN_TAIL=1 timeout 600 python tools/bench_ops.py --what attention --out gpurun_out/r02b_attn_token1_helper_tail1.json >> gpurun_out/r02b_ops.log 2>&1
 for p in 0 2; do
   echo "TAIL=1 POLY=$p" >> gpurun_out/r02b_ops.log
   MHMR_ATTN_TAIL=1 MHMR_ATTN_POLY=$p timeout 600 python tools/bench_ops.py --what attention --out gpurun_out/r02b_attn_tail_poly$p.json >> gpurun_out/r02b_ops.log 2>&1
 done
-grep 'attention\|POLY\|TAIL\|HELPER' gpurun_out/r02b_ops.log
+grep 'attention\|POLY\|TAIL\|HELPER\|TOKEN' gpurun_out/r02b_ops.log
 timeout 1800 python -m pytest tests -m gpu -q -s --deselect tests/test_attention_gpu.py > gpurun_out/r02b_pytest.log 2>&1
 grep -n "passed\|failed" gpurun_out/r02b_pytest.log | tail -3
 if grep -q "failed" gpurun_out/r02b_pytest.log; then

@@ -17,10 +17,24 @@ for path in sorted(glob.glob("gpurun_out/r02b_attn_*.json")):
     env = {"new": "MHMR_ATTN_V1=0", "v1": "MHMR_ATTN_V1=1", "poly1": "MHMR_ATTN_V1=0 MHMR_ATTN_POLY=1",
            "poly2": "MHMR_ATTN_V1=0 MHMR_ATTN_POLY=2", "poly3": "MHMR_ATTN_V1=0 MHMR_ATTN_POLY=3",
            "tail_poly0": "MHMR_ATTN_V1=0 MHMR_ATTN_TAIL=1", "tail_poly2": "MHMR_ATTN_V1=0 MHMR_ATTN_TAIL=1 MHMR_ATTN_POLY=2",
-           "helper_tail0": "MHMR_ATTN_V1=0 MHMR_ATTN_HELPER=1", "helper_tail1": "MHMR_ATTN_V1=0 MHMR_ATTN_HELPER=1 MHMR_ATTN_TAIL=1"}.get(tag)
+           "helper_tail0": "MHMR_ATTN_V1=0 MHMR_ATTN_HELPER=1", "helper_tail1": "MHMR_ATTN_V1=0 MHMR_ATTN_HELPER=1 MHMR_ATTN_TAIL=1",
+           "token1_tail1": "MHMR_ATTN_V1=0 MHMR_ATTN_TOKEN=1 MHMR_ATTN_TAIL=1",
+           "token2_tail1": "MHMR_ATTN_V1=0 MHMR_ATTN_TOKEN=2 MHMR_ATTN_TAIL=1",
+           "token1_helper_tail1": "MHMR_ATTN_V1=0 MHMR_ATTN_TOKEN=1 MHMR_ATTN_HELPER=1 MHMR_ATTN_TAIL=1"}.get(tag)
     if env is None:
         continue
     # a variant only qualifies if its unit tests passed
+    need = {"token1_tail1": ["token_test", "tail_test"], "token2_tail1": ["token_test", "tail_test"],
+            "token1_helper_tail1": ["token_test", "tail_test", "helper_test"]}.get(tag)
+    if need is not None:
+        ok_all = True
+        for lg in need:
+            pth = f"gpurun_out/r02b_attn_{lg}.log"
+            txt = open(pth).read() if os.path.exists(pth) else "failed"
+            ok_all = ok_all and ("failed" not in txt) and ("passed" in txt)
+        if ok_all and (best is None or ms < best[0]):
+            best = (ms, env, tag)
+        continue
     log = {"poly1": "poly2_test", "poly2": "poly2_test", "poly3": "poly2_test", "tail_poly0": "tail_test",
            "tail_poly2": "tail_test", "helper_tail0": "helper_test", "helper_tail1": "helper_test"}.get(tag)
     ok = True
