@@ -92,3 +92,23 @@ def test_fused_uint8_loader_equals_normalize_then_forward(cuda_device):
         b = m(u8.to(cuda_device), idx=idx, K=K, is_training=True)
         for k in ("scores", "v3d", "rotmat", "shape", "dist", "loc", "j2d", "offset"):
             assert torch.equal(a[k], b[k]), (refine, k)
+
+
+@pytest.mark.gpu
+def test_host_batch_loader_hands_over_the_submitted_batch(cuda_device):
+    """api.HostBatchLoader: the batch submitted on the copy stream arrives intact on the compute stream, two batches
+    in flight never alias."""
+    from multihmr_b200 import api, synth
+
+    loader = api.HostBatchLoader(cuda_device)
+    a = synth.make_images_u8(2, 224, seed=1).pin_memory()
+    b = synth.make_images_u8(2, 224, seed=2).pin_memory()
+    K = synth.make_cameras(2, 224, seed=1).pin_memory()
+    loader.submit(a, K)
+    xa, Ka = loader.get()
+    loader.submit(b, K)
+    assert not loader._pending is None and loader.pending
+    xb, _ = loader.get()
+    torch.cuda.synchronize()
+    assert torch.equal(xa.cpu(), a) and torch.equal(xb.cpu(), b) and torch.equal(Ka.cpu(), K)
+    assert xa.data_ptr() != xb.data_ptr()

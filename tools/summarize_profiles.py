@@ -64,4 +64,23 @@ with open(os.path.join(out_dir, f"{tag}_kernels_full.md"), "w") as fh:
             except ValueError:
                 vals.append(v)
         fh.write(f"| `{k}` | " + " | ".join(vals) + " |\n")
+# DRAM traffic per launch of the dominant kernels -> profiles/ncu_traffic.json (read by bench.py for roofline.traffic)
+import json
+
+fam = {"attn_fwd_kernel": "attention", "gemm_tc2_kernel<0>": "gemm_qkv", "gemm_tc2_kernel<1>": "gemm_fc1",
+       "gemm_tc2_kernel<3>": "gemm_proj"}
+traffic = {"_source": f"profiles/{tag}_kernels_full.md (ncu --set full --clock-control none, first captured launch of each "
+                      f"kernel, multiHMR_896_L batch 8)"}
+seen = set()
+for r in rows[2:]:
+    k = short(r[ix["Kernel Name"]])
+    for prefix, name in fam.items():
+        if k.startswith(prefix) and name not in seen:
+            seen.add(name)
+            def val(metric):
+                v, u = float(r[ix[metric]]), rows[1][ix[metric]]
+                return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            traffic[name] = {"dram_bytes_per_launch": int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum")),
+                             "kernel": k}
+json.dump(traffic, open(os.path.join(out_dir, "ncu_traffic.json"), "w"), indent=1)
 print("wrote", os.listdir(out_dir))
