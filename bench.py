@@ -358,6 +358,8 @@ def run_ours(args):
                                                     / (ms2 / 1e3) / 1e12 / measured_peaks()["tflops"], 4)}
         del b2
 
+    if world > 1:
+        bench.sharded.close()   # the library's own NCCL communicator
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -67,10 +67,8 @@ constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: Q, K or V tile
 constexpr int kBarrierBytes = 512;              // mbarriers + the TMEM slot
 constexpr int kStagesK = 4, kStagesV = 4;
 constexpr int kQTiles = 4;    // two items x two query tiles
-constexpr int kDefaultPoly = 0;      // default MHMR_ATTN_POLY level
-constexpr int kDefaultUseV1 = 1;     // 1 until the persistent kernel is validated on hardware (MHMR_ATTN_V1=0 selects it)
+constexpr int kDefaultUseV1 = 0;     // MHMR_ATTN_V1=1 selects the round-1 kernel (A/B timing)
 constexpr int kDefaultToken = 0;     // default MHMR_ATTN_TOKEN (0: mbarrier token)
-constexpr int kDefaultHelper = 0;    // default MHMR_ATTN_HELPER (1: polynomial-exponential helper warps)
 constexpr int kDefaultSimtTail = 0;  // default MHMR_ATTN_TAIL (1: ragged tail rows on the idle warps)
 constexpr int kPassAt = 112;  // exponentials issued before the MUFU token is handed on (measured optimum)
 
@@ -96,29 +94,8 @@ __device__ __forceinline__ uint32_t clk_after(float dep) {
   return t;
 }
 
-// exp2 of two exponent arguments on the FMA / ALU pipes (no MUFU): round-to-nearest range reduction with the
-// 1.5 * 2^23 trick, degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (relative error 7.5e-5, below the 4.9e-4 of the
-// fp16 rounding P gets anyway), exponent inserted with an integer shift-add.  10 instructions per pair.
-__device__ __forceinline__ float2 exp2_poly2(float2 x) {
-  const float2 xc = make_float2(fmaxf(x.x, -125.0f), fmaxf(x.y, -125.0f));
-  const float2 magic = make_float2(12582912.0f, 12582912.0f);
-  const float2 t = __fadd2_rn(xc, magic);
-  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), xc);
-  float2 p = __ffma2_rn(make_float2(0.0551716685295105f, 0.0551716685295105f), f,
-                        make_float2(0.2426111251115799f, 0.2426111251115799f));
-  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
-  p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
-  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
-  return r;
-}
-
-constexpr int kAttnThreads = 384, kAttnThreadsHelp = 512;
+constexpr int kAttnThreads = 384;
 constexpr int kRegsIssue = 88, kRegsSoftmax = 208;  // 128 * (88 + 2 * 208) <= 64 K registers
-constexpr int kRegsSoftmaxHelp = 168, kRegsHelper = 88;  // with helper warps: 128 * (88 + 2 * 168 + 88) = 64 K
-constexpr int kHelpCols = 32;  // score columns per key tile handled by a helper warp (the last chunk)
 // Q tiles + K ring + V ring + 1 KB that covers both the 1024-byte alignment of the tiles and the barriers
 // (in front of the tiles when the alignment pad leaves room, behind them otherwise)
 constexpr int attn_smem_bytes(int sk, int sv) { return kTileBytes * (kQTiles + sk + sv) + 1024; }
@@ -147,19 +124,11 @@ __device__ __forceinline__ AttnItem attn_decode_item(int idx, int n_qp, int head
   return it;
 }
 
-// kPolyMask: which of the 32 scores of a chunk get their exponential from exp2_poly2 instead of MUFU.EX2 (pairs of
-// adjacent bits).  MUFU.EX2 issues once per 8 clk per sub-partition; the warp that owns the MUFU token has idle issue
-// slots in between, and the polynomial pairs are woven into them: fewer MUFU instructions per key tile.
-// kHelp: four extra warps (12-15, one per TMEM lane quarter) take the last 32 score columns of BOTH query tiles off the
-// MUFU: they compute those exponentials with exp2_poly2 on the FMA / ALU pipes concurrently with the MUFU runs of the
-// softmax warps (different warps: the hardware scheduler interleaves them, no ptxas scheduling games).  The softmax
-// warp of a (tile, quarter) still takes the row max over all 128 columns and publishes the exponent offset through
-// shared memory; the helper keeps the partial row sums of its columns and hands them over at the end of an item.
-// kTok = 1: the MUFU token travels through named barriers (bar.arrive / bar.sync, ids 2..9) instead of mbarriers:
-// the timeline shows ~340 clk between the mbarrier arrive and the partner's first exponential (the arrive queues behind
-// the MUFU instructions in flight and the waiter wakes up late); kPass = exponentials issued before the hand-over.
-template <int kSK, int kSV, int kAb = 0, uint32_t kPolyMask = 0u, int kHelp = 0, int kTok = 0, int kPass = kPassAt>
-__global__ void __launch_bounds__(kHelp ? kAttnThreadsHelp : kAttnThreads, 1)
+// kTok = 1: the MUFU token travels through named barriers (bar.arrive / bar.sync, ids 2..9) instead of mbarriers
+// (experiment, MHMR_ATTN_TOKEN): the timeline shows ~340 clk between the mbarrier arrive and the partner's first
+// exponential.  kPass = exponentials issued before the hand-over.
+template <int kSK, int kSV, int kAb = 0, int kTok = 0, int kPass = kPassAt>
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restrict__ qkv, int64_t ld_qkv,
                 __half* __restrict__ out, int64_t ldo, int T, int D, int heads, int bh, int n_qp, int n_items,
                 int tail_rows, float scale_log2) {
@@ -185,12 +154,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
   // partner's MUFU.EX2 and the kernel gets 8 % slower.)
   uint64_t* turn_a = pv_done + 2;          // [4]    tile-0 warp -> tile-1 warp of a sub-partition: exps done
   uint64_t* turn_b = turn_a + 4;           // [4]    tile-1 warp -> tile-0 warp: exps done
-  uint64_t* m_ready = turn_b + 4;          // [2][4] softmax (tile, quarter) -> helper: exponent offset of this key tile published
-  uint64_t* l_ready = m_ready + 8;         // [2][4] helper -> softmax (tile, quarter): partial row sums of the item published
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_ready + 8);
-  static_assert((4 + 2 * kSK + 2 * kSV + 32) * 8 + 4 <= kBarrierBytes, "barrier area too small");
-  __shared__ float m_buf[2][2][kHelp ? 128 : 1];  // [key-tile parity][query tile][row]: exponent offset (log2 domain)
-  __shared__ float l_buf[2][kHelp ? 128 : 1];     // [query tile][row]: helper's partial row sums of the item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn_b + 4);
+  static_assert((4 + 2 * kSK + 2 * kSV + 16) * 8 + 4 <= kBarrierBytes, "barrier area too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -217,17 +182,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
       }
       for (int t = 0; t < 2; ++t) {
         mbar_init(&s_full[t], 1);
-        mbar_init(&s_empty[t], kHelp ? 8 : 4);
-        mbar_init(&p_full[t], kHelp ? 8 : 4);
+        mbar_init(&s_empty[t], 4);
+        mbar_init(&p_full[t], 4);
         mbar_init(&pv_done[t], 1);
       }
       for (int q = 0; q < 4; ++q) {
         mbar_init(&turn_a[q], 1);
         mbar_init(&turn_b[q], 1);
-      }
-      for (int q = 0; q < 8; ++q) {
-        mbar_init(&m_ready[q], 1);
-        mbar_init(&l_ready[q], 1);
       }
       fence_barrier_init();
     }
@@ -399,7 +360,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
         constexpr int kU = 4;  // keys in flight per lane group
-        for (int k0 = w2 * 4 + grp; k0 < T; k0 += 8 * kU) {
+        // warp-uniform trip count (the shuffles below need every lane): the loop runs over 32-key blocks, each lane
+        // group takes key kb + w2 * 4 + grp + 8 u of the block and masks the keys beyond T
+        for (int kb = 0; kb < T; kb += 8 * kU) {
+          const int k0 = kb + w2 * 4 + grp;
           uint4 kk[kU], vv[kU];
 #pragma unroll
           for (int u = 0; u < kU; ++u) {
@@ -478,101 +442,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
         asm volatile("bar.sync 1, 64;" ::: "memory");  // the scratch is free for the next task
       }
     }
-  } else if (kHelp && warp >= 12) {
-    // ------------------------------ Helper warps (polynomial exponentials) -------
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsHelper));
-    const int hs = warp & 3;
-    const int row = hs * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(hs * 32) << 16;
-    const int last_nch = (last_cols + 31) >> 5;
-    uint32_t n_ht[2] = {0u, 0u};  // key tiles seen per query tile (all items)
-    uint32_t n_hi[2] = {0u, 0u};  // items finished per query tile
-    for (int item = first_item; item < n_items; item += item_stride) {
-      const AttnItem a = attn_decode_item(item, n_qp, heads, bh, T);
-      float lh[2] = {0.f, 0.f}, m_prev[2] = {-INFINITY, -INFINITY};
-      for (int j = 0; j < n_kv; ++j) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (t == 1 && !a.two) continue;
-          const uint32_t cnt = n_ht[t] + j;
-          const bool has_rows = (a.q0 + t * kBlockQ + hs * 32) < T;
-          const bool last = (j == n_kv - 1);
-          const bool active = has_rows && (!last || last_nch == 4);  // this tile has columns 96..127
-          const uint32_t t_s = tmem_base + lane_base + t * 256 + kColS + (128 - kHelpCols);
-          const uint32_t t_p = tmem_base + lane_base + t * 256 + kColP + (128 - kHelpCols) / 2;
-          uint32_t s[32];
-          mbar_wait(&s_full[t], cnt & 1u);
-          tc_fence_after();
-          if (active) {
-            tmem_ld_32x32(t_s, s);
-            tmem_ld_wait();
-            tc_fence_before();
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[t]);
-          mbar_wait(&m_ready[t * 4 + hs], cnt & 1u);
-          uint32_t p[16];
-          if (active) {
-            const float m = m_buf[cnt & 1u][t][row];
-            if (m != m_prev[t]) {
-              lh[t] *= exp2f(m_prev[t] - m);  // 0 on the first tile
-              m_prev[t] = m;
-            }
-            if (last) {
-#pragma unroll
-              for (int k = 0; k < 32; ++k)
-                if (96 + k >= last_valid) s[k] = 0xff800000u;
-            }
-            const float2 sc2 = make_float2(scale_log2, scale_log2);
-            const float2 nm2 = make_float2(-m, -m);
-            float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-              const float2 a0 = __ffma2_rn(make_float2(__uint_as_float(s[k]), __uint_as_float(s[k + 1])), sc2, nm2);
-              const float2 a1 = __ffma2_rn(make_float2(__uint_as_float(s[k + 2]), __uint_as_float(s[k + 3])), sc2, nm2);
-              const float2 e0 = exp2_poly2(a0), e1 = exp2_poly2(a1);
-              acc0 = __fadd2_rn(acc0, e0);
-              acc1 = __fadd2_rn(acc1, e1);
-              const __half2 h0 = __floats2half2_rn(e0.x, e0.y), h1 = __floats2half2_rn(e1.x, e1.y);
-              p[k / 2] = *reinterpret_cast<const uint32_t*>(&h0);
-              p[k / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-            }
-            lh[t] += (acc0.x + acc0.y) + (acc1.x + acc1.y);
-          }
-          // the P buffer is free once the previous P V of this query tile is complete (see the softmax warps)
-          if (j + 1 < n_kv) {
-            mbar_wait(&s_full[t], (cnt + 1u) & 1u);
-          } else if (cnt > 0) {
-            mbar_wait(&pv_done[t], (cnt - 1u) & 1u);
-          }
-          tc_fence_after();
-          if (active) {
-            tmem_st_32x16(t_p, p);
-            tmem_st_wait();
-            tc_fence_before();
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[t]);
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (t == 1 && !a.two) continue;
-        l_buf[t][row] = lh[t];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&l_ready[t * 4 + hs]);
-        mbar_wait(&pv_done[t], (n_ht[t] + n_kv - 1u) & 1u);
-        n_ht[t] += n_kv;
-        ++n_hi[t];
-      }
-    }
   } else {
     // ------------------------------ Softmax warps ------------------------------
-    if constexpr (kHelp) {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmaxHelp));
-    } else {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
-    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
     const int t = (warp - 4) >> 2;        // query tile of this warp
     const int sub = warp & 3;             // TMEM sub-partition (lane quarter) = SM sub-partition of this warp
     const int row = sub * 32 + lane;
@@ -588,7 +460,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
     uint64_t* turn_pass = (t == 0) ? &turn_a[sub] : &turn_b[sub];
     uint32_t n_t = 0;   // key tiles this warp's query tile has been through (all items): phase of s_full / pv_done
     uint32_t n_tok = 0; // tokens this warp has passed on (two-tile items only)
-    uint32_t n_it = 0;  // items this warp's query tile has finished (phase of l_ready)
     const int last_nch = (last_cols + 31) >> 5;  // 32-column chunks of the last tile that hold real keys
     const bool tracer_warp = kTrace && sub == 0 && lane == 0;
 
@@ -634,10 +505,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
         for (int j = 0; j < n_kv; ++j) {
           mbar_wait(my_s_full, (nb + j) & 1u);
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(my_s_empty);
-            if constexpr (kHelp) mbar_arrive(&m_ready[t * 4 + sub]);
-          }
+          if (lane == 0) mbar_arrive(my_s_empty);
           take_turn();
           pass_turn();
           // arrive on p_full only once the previous P V of this query tile is over: this warp runs ahead of the
@@ -648,7 +516,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
         }
         mbar_wait(my_pv_done, (nb + n_kv - 1u) & 1u);
         n_t = nb + n_kv;
-        ++n_it;
         continue;
       }
 
@@ -662,7 +529,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
       auto softmax_tile = [&](auto nch_c, auto last_c, int j) {
         constexpr int NCH = decltype(nch_c)::value;
         constexpr bool kLast = decltype(last_c)::value;  // static: the key mask costs 2 instructions per score
-        constexpr int NM = (kHelp && NCH == 4) ? 3 : NCH;  // chunks exponentiated here (the helper warp takes the last)
         uint32_t s[NCH][32];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
@@ -697,16 +563,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
           alpha = exp2f(m_used - m_new);  // 0 on the first tile
           m_used = m_new;
         }
-        if constexpr (kHelp) {  // publish the exponent offset of this key tile to the helper warp of this quarter
-          m_buf[(nb + j) & 1u][t][row] = m_used;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&m_ready[t * 4 + sub]);
-        }
         // (A) exponent arguments, in place
         const float2 sc2 = make_float2(scale_log2, scale_log2);
         const float2 nm2 = make_float2(-m_used, -m_used);
 #pragma unroll
-        for (int c = 0; c < NM; ++c) {
+        for (int c = 0; c < NCH; ++c) {
 #pragma unroll
           for (int k = 0; k < 32; k += 2) {
             const float2 a2 = __ffma2_rn(make_float2(__uint_as_float(s[c][k]), __uint_as_float(s[c][k + 1])), sc2, nm2);
@@ -725,49 +586,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
         take_turn();
         if (tracer) stamp(j, t * 8 + 2, 0.f);
 #pragma unroll
-        for (int c = 0; c < NM; ++c) {
+        for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            // MUFU.EX2 first (they queue up in the MUFU pipe, one per 8 clk), then the polynomial pairs of this
-            // half-chunk on the FMA / ALU pipes while the queue drains
-#pragma unroll
-            for (int k = h * 16; k < h * 16 + 16; ++k) {
-              if constexpr (kAb != 1 && kAb != 4) {
-                if (!((kPolyMask >> k) & 1u)) {
-                  float e;
-                  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(s[c][k])));
-                  s[c][k] = __float_as_uint(e);
-                }
-              }
-              // hand the token on kPassAt exponentials into the run (full tiles; at the end of a short last tile):
-              // the partner needs ~150 clk to wake up, its first exponentials then overlap this warp's last ones
-              if ((NCH == 4 && c * 32 + k + 1 == (kHelp ? kPass - kHelpCols : kPass)) ||
-                  (NCH < 4 && c == NCH - 1 && k == 31)) {
-                if (opaque_true()) pass_turn();
-              }
+          for (int k = 0; k < 32; ++k) {
+            if constexpr (kAb != 1 && kAb != 4) {
+              float e;
+              asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(s[c][k])));
+              s[c][k] = __float_as_uint(e);
             }
-            if constexpr (kPolyMask != 0u && kAb != 1 && kAb != 4) {
-#pragma unroll
-              for (int k = h * 16; k < h * 16 + 16; k += 2) {
-                if ((kPolyMask >> k) & 1u) {
-                  const float2 e2 = exp2_poly2(make_float2(__uint_as_float(s[c][k]), __uint_as_float(s[c][k + 1])));
-                  s[c][k] = __float_as_uint(e2.x);
-                  s[c][k + 1] = __float_as_uint(e2.y);
-                }
-              }
-              // scheduling fence: ptxas would otherwise hoist every MUFU of the tile in front of all the
-              // polynomial work (in-order issue would then serialise the two)
-              if (!opaque_true()) return;
+            // hand the token on kPassAt exponentials into the run (full tiles; at the end of a short last tile):
+            // the partner needs ~150 clk to wake up, its first exponentials then overlap this warp's last ones
+            if ((NCH == 4 && c * 32 + k + 1 == kPass) || (NCH < 4 && c == NCH - 1 && k == 31)) {
+              if (opaque_true()) pass_turn();
             }
           }
         }
-        if (tracer) stamp(j, t * 8 + 3, __uint_as_float(s[NM - 1][31]));
+        if (tracer) stamp(j, t * 8 + 3, __uint_as_float(s[NCH - 1][31]));
         // (C) row sum and fp16 packing -- in a block of its own, so that it is not woven into the MUFU run
         if (!opaque_true()) return;
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-        uint32_t p[NM][16];
+        uint32_t p[NCH][16];
 #pragma unroll
-        for (int c = 0; c < NM; ++c) {
+        for (int c = 0; c < NCH; ++c) {
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
             const float2 e0 = make_float2(__uint_as_float(s[c][k]), __uint_as_float(s[c][k + 1]));
@@ -803,7 +643,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
           }
         }
 #pragma unroll
-        for (int c = 0; c < NM; ++c) tmem_st_32x16(t_p + c * 16, p[c]);
+        for (int c = 0; c < NCH; ++c) tmem_st_32x16(t_p + c * 16, p[c]);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -825,10 +665,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
       // O; it is gated by this warp's next arrival on p_full, which comes after these loads.
       mbar_wait(my_pv_done, (nb + n_kv - 1u) & 1u);
       tc_fence_after();
-      if constexpr (kHelp) {
-        mbar_wait(&l_ready[t * 4 + sub], n_it & 1u);
-        l += l_buf[t][row];
-      }
       const float inv_l = 1.0f / l;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -852,7 +688,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
       }
       tc_fence_before();
       n_t = nb + n_kv;
-      ++n_it;
     }
   }
 
@@ -878,17 +713,17 @@ struct AttnArgs {
   cudaStream_t stream;
 };
 
-template <int kAb, uint32_t kPolyMask = 0u, int kHelp = 0, int kTok = 0, int kPass = kPassAt>
+template <int kAb, int kTok = 0, int kPass = kPassAt>
 int attn_launch(const AttnArgs& a) {
   constexpr int smem = attn_smem_bytes(kStagesK, kStagesV);
-  auto kern = attn_fwd_kernel<kStagesK, kStagesV, kAb, kPolyMask, kHelp, kTok, kPass>;
+  auto kern = attn_fwd_kernel<kStagesK, kStagesV, kAb, kTok, kPass>;
   static PerDeviceOnce once;
   if (once.first()) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(a.grid);
-  cfg.blockDim = dim3(kHelp ? kAttnThreadsHelp : kAttnThreads);
+  cfg.blockDim = dim3(kAttnThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = a.stream;
   cudaLaunchAttribute attr[1];
@@ -972,30 +807,13 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
     MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &d_trace, sizeof(d_trace)));
     return MHMR_OK;
   }
-  static int poly = -1;  // MHMR_ATTN_POLY: share of the exponentials computed on the FMA pipes (experiments)
-  if (poly < 0) {
-    const char* pe = std::getenv("MHMR_ATTN_POLY");
-    poly = (pe != nullptr) ? atoi(pe) : kDefaultPoly;
-  }
-  static int helper = -1;  // MHMR_ATTN_HELPER: polynomial-exponential helper warps
-  if (helper < 0) {
-    const char* he = std::getenv("MHMR_ATTN_HELPER");
-    helper = (he != nullptr) ? atoi(he) : kDefaultHelper;
-  }
   static int tok = -1;  // MHMR_ATTN_TOKEN: 1 / 2 = named-barrier MUFU token, handed on after 112 / 124 exponentials
   if (tok < 0) {
     const char* tk = std::getenv("MHMR_ATTN_TOKEN");
     tok = (tk != nullptr) ? atoi(tk) : kDefaultToken;
   }
-  if (helper != 0) return tok ? attn_launch<0, 0u, 1, 1, 120>(a) : attn_launch<0, 0u, 1>(a);
-  if (tok == 1) return attn_launch<0, 0u, 0, 1, 112>(a);
-  if (tok == 2) return attn_launch<0, 0u, 0, 1, 124>(a);
-  switch (poly) {
-    case 1: return attn_launch<0, 0xC000C000u>(a);   // 4 of 32
-    case 2: return attn_launch<0, 0xC0C0C0C0u>(a);   // 8 of 32
-    case 3: return attn_launch<0, 0xCC30CC30u>(a);   // 12 of 32
-    default: break;
-  }
+  if (tok == 1) return attn_launch<0, 1, 112>(a);
+  if (tok == 2) return attn_launch<0, 1, 124>(a);
   return attn_launch<0>(a);
 }
 

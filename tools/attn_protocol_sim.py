@@ -34,7 +34,7 @@ class Wait:
         self.bar, self.index = bar, index  # index = the completion (0-based) the waiter means; -1 = "fresh pass"
 
 
-def simulate(items, n_kv, rows_of, seed=0, verbose=False, helpers=False):
+def simulate(items, n_kv, rows_of, seed=0, verbose=False):
     """items: list of bool (two-tile?) for ONE CTA in order.  rows_of(item, t, sub) -> bool (warp has rows)."""
     rnd = random.Random(seed)
     B = {}
@@ -46,11 +46,8 @@ def simulate(items, n_kv, rows_of, seed=0, verbose=False, helpers=False):
     for s in range(V_STAGES):
         B[f"v_full{s}"], B[f"v_empty{s}"] = Bar(f"v_full{s}", 1), Bar(f"v_empty{s}", 1)
     for t in range(2):
-        nw = 8 if helpers else 4
-        B[f"s_full{t}"], B[f"s_empty{t}"] = Bar(f"s_full{t}", 1), Bar(f"s_empty{t}", nw)
-        B[f"p_full{t}"], B[f"pv_done{t}"] = Bar(f"p_full{t}", nw), Bar(f"pv_done{t}", 1)
-        for q in range(4):
-            B[f"m_ready{t}{q}"], B[f"l_ready{t}{q}"] = Bar(f"m_ready{t}{q}", 1), Bar(f"l_ready{t}{q}", 1)
+        B[f"s_full{t}"], B[f"s_empty{t}"] = Bar(f"s_full{t}", 1), Bar(f"s_empty{t}", 4)
+        B[f"p_full{t}"], B[f"pv_done{t}"] = Bar(f"p_full{t}", 4), Bar(f"pv_done{t}", 1)
     for q in range(4):
         B[f"turn_a{q}"], B[f"turn_b{q}"] = Bar(f"turn_a{q}", 1), Bar(f"turn_b{q}", 1)
 
@@ -157,7 +154,7 @@ def simulate(items, n_kv, rows_of, seed=0, verbose=False, helpers=False):
             it += 1
 
     def softmax(t, sub):
-        n_t, n_tok, n_it = 0, 0, 0
+        n_t, n_tok = 0, 0
         for seq, two in enumerate(items):
             if t == 1 and not two:
                 continue
@@ -176,8 +173,6 @@ def simulate(items, n_kv, rows_of, seed=0, verbose=False, helpers=False):
                 for j in range(n_kv):
                     yield wait(f"s_full{t}", nb + j)
                     B[f"s_empty{t}"].arrive()
-                    if helpers:
-                        B[f"m_ready{t}{sub}"].arrive()
                     yield from take_turn()
                     if two:
                         B[f"turn_{'a' if t == 0 else 'b'}{sub}"].arrive()
@@ -187,14 +182,11 @@ def simulate(items, n_kv, rows_of, seed=0, verbose=False, helpers=False):
                     B[f"p_full{t}"].arrive()
                 yield wait(f"pv_done{t}", nb + n_kv - 1)
                 n_t = nb + n_kv
-                n_it += 1
                 continue
             yield wait(f"s_full{t}", nb)
             for j in range(n_kv):
                 assert state["S"][t] == (seq, j), f"softmax t{t} sub{sub} item {seq} tile {j} reads S = {state['S'][t]}"
                 B[f"s_empty{t}"].arrive()
-                if helpers:
-                    B[f"m_ready{t}{sub}"].arrive()
                 yield from take_turn()
                 yield ("work", rnd.randint(1, 10))
                 if two:
@@ -209,43 +201,13 @@ def simulate(items, n_kv, rows_of, seed=0, verbose=False, helpers=False):
                 state["P"][t] = (seq, j)
                 B[f"p_full{t}"].arrive()
             yield wait(f"pv_done{t}", nb + n_kv - 1)
-            if helpers:
-                yield wait(f"l_ready{t}{sub}", n_it)
             yield ("work", rnd.randint(1, 5))  # epilogue reads O
             n_t = nb + n_kv
-            n_it += 1
-
-    def helper(hs):
-        n_ht = [0, 0]
-        for seq, two in enumerate(items):
-            for j in range(n_kv):
-                for t in range(2):
-                    if t == 1 and not two:
-                        continue
-                    cnt = n_ht[t] + j
-                    yield wait(f"s_full{t}", cnt)
-                    B[f"s_empty{t}"].arrive()
-                    yield wait(f"m_ready{t}{hs}", cnt)
-                    yield ("work", rnd.randint(1, 8))
-                    if j + 1 < n_kv:
-                        yield wait(f"s_full{t}", cnt + 1)
-                    elif cnt > 0:
-                        yield wait(f"pv_done{t}", cnt - 1)
-                    B[f"p_full{t}"].arrive()
-            for t in range(2):
-                if t == 1 and not two:
-                    continue
-                B[f"l_ready{t}{hs}"].arrive()
-                yield wait(f"pv_done{t}", n_ht[t] + n_kv - 1)
-                n_ht[t] += n_kv
 
     roles = {"tma": tma(), "mma": mma()}
     for t in range(2):
         for sub in range(4):
             roles[f"sm{t}{sub}"] = softmax(t, sub)
-    if helpers:
-        for hs in range(4):
-            roles[f"help{hs}"] = helper(hs)
     blocked = {}      # role -> Wait
     sleeping = {}     # role -> wake time
     done = set()
@@ -318,8 +280,7 @@ def main():
                     return not (t == 1 and sub >= 1 and seq == len(items) - 1)   # last item's tile 1 has 17 rows
                 for seed in range(3):
                     simulate(list(items), n_kv, rows_of, seed=seed)
-                    simulate(list(items), n_kv, rows_of, seed=seed, helpers=True)
-                    n += 2
+                    n += 1
     print(f"attention barrier protocol: {n} simulated schedules, no deadlock, no parity aliasing, no buffer hazard")
 
 
