@@ -68,8 +68,7 @@ constexpr int kBarrierBytes = 512;              // mbarriers + the TMEM slot
 constexpr int kStagesK = 4, kStagesV = 4;
 constexpr int kQTiles = 4;    // two items x two query tiles
 constexpr int kDefaultUseV1 = 0;     // MHMR_ATTN_V1=1 selects the round-1 kernel (A/B timing)
-constexpr int kDefaultToken = 0;     // default MHMR_ATTN_TOKEN (0: mbarrier token)
-constexpr int kDefaultSimtTail = 0;  // default MHMR_ATTN_TAIL (1: ragged tail rows on the idle warps)
+constexpr int kDefaultSimtTail = -1; // MHMR_ATTN_TAIL: 1 / 0 force the SIMT tail rows on / off, -1 = decide per problem
 constexpr int kPassAt = 112;  // exponentials issued before the MUFU token is handed on (measured optimum)
 
 constexpr uint32_t kColS = 0;
@@ -124,10 +123,7 @@ __device__ __forceinline__ AttnItem attn_decode_item(int idx, int n_qp, int head
   return it;
 }
 
-// kTok = 1: the MUFU token travels through named barriers (bar.arrive / bar.sync, ids 2..9) instead of mbarriers
-// (experiment, MHMR_ATTN_TOKEN): the timeline shows ~340 clk between the mbarrier arrive and the partner's first
-// exponential.  kPass = exponentials issued before the hand-over.
-template <int kSK, int kSV, int kAb = 0, int kTok = 0, int kPass = kPassAt>
+template <int kSK, int kSV, int kAb = 0>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restrict__ qkv, int64_t ld_qkv,
                 __half* __restrict__ out, int64_t ldo, int T, int D, int heads, int bh, int n_qp, int n_items,
@@ -476,25 +472,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
       // exps(tile 0) of the same key tile
       auto take_turn = [&]() {
         if (two) {
-          if constexpr (kTok == 1) {
-            if (t == 1 || n_tok > 0) asm volatile("bar.sync %0, 64;" ::"r"(t == 0 ? 6 + sub : 2 + sub) : "memory");
+          if (t == 0) {
+            if (n_tok > 0) mbar_wait(turn_wait, (n_tok - 1u) & 1u);
           } else {
-            if (t == 0) {
-              if (n_tok > 0) mbar_wait(turn_wait, (n_tok - 1u) & 1u);
-            } else {
-              mbar_wait(turn_wait, n_tok & 1u);
-            }
+            mbar_wait(turn_wait, n_tok & 1u);
           }
         }
       };
       auto pass_turn = [&]() {
         if (two) {
-          if constexpr (kTok == 1) {
-            asm volatile("bar.arrive %0, 64;" ::"r"(t == 0 ? 2 + sub : 6 + sub) : "memory");
-          } else {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(turn_pass);
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(turn_pass);
           ++n_tok;
         }
       };
@@ -596,7 +584,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
             }
             // hand the token on kPassAt exponentials into the run (full tiles; at the end of a short last tile):
             // the partner needs ~150 clk to wake up, its first exponentials then overlap this warp's last ones
-            if ((NCH == 4 && c * 32 + k + 1 == kPass) || (NCH < 4 && c == NCH - 1 && k == 31)) {
+            if ((NCH == 4 && c * 32 + k + 1 == kPassAt) || (NCH < 4 && c == NCH - 1 && k == 31)) {
               if (opaque_true()) pass_turn();
             }
           }
@@ -713,10 +701,10 @@ struct AttnArgs {
   cudaStream_t stream;
 };
 
-template <int kAb, int kTok = 0, int kPass = kPassAt>
+template <int kAb>
 int attn_launch(const AttnArgs& a) {
   constexpr int smem = attn_smem_bytes(kStagesK, kStagesV);
-  auto kern = attn_fwd_kernel<kStagesK, kStagesV, kAb, kTok, kPass>;
+  auto kern = attn_fwd_kernel<kStagesK, kStagesV, kAb>;
   static PerDeviceOnce once;
   if (once.first()) {
     MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -777,7 +765,21 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
     simt_tail = (te != nullptr) ? atoi(te) : kDefaultSimtTail;
   }
   const int rem = T % (2 * kBlockQ);
-  a.tail_rows = (simt_tail != 0 && rem >= 1 && rem <= 32) ? rem : 0;
+  bool use_tail = (simt_tail != 0 && rem >= 1 && rem <= 32);
+  if (use_tail && simt_tail < 0) {
+    // The tail warps share two sub-partitions' issue slots with softmax warps: worth it only while their work is a
+    // few per cent of the CTA's lifetime (measured r02e: -4.7 % at 896 / batch 8, +11 % at 672 / batch 4).
+    // ~200 issue-clk per 32 keys and row; ~2500 clk per key tile of an item.
+    const int sms = device_sm_count();
+    const int64_t n_full = static_cast<int64_t>(a.bh) * (T / (2 * kBlockQ));
+    const int64_t grid = n_full < sms ? (n_full > 0 ? n_full : 1) : sms;
+    const int64_t tasks_per_cta = (static_cast<int64_t>(a.bh) * rem + grid - 1) / grid;
+    const int64_t items_per_cta = (n_full + grid - 1) / grid;
+    const int64_t tail_cost = tasks_per_cta * ((T + 31) / 32) * 200;
+    const int64_t lifetime = items_per_cta * ((T + kBlockKV - 1) / kBlockKV) * 2500;
+    use_tail = n_full > 0 && tail_cost * 100 < lifetime * 3;
+  }
+  a.tail_rows = use_tail ? rem : 0;
   a.n_qp = (a.tail_rows > 0) ? T / (2 * kBlockQ) : (T + 2 * kBlockQ - 1) / (2 * kBlockQ);
   a.n_items = a.bh * a.n_qp;
   a.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
@@ -807,13 +809,6 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
     MHMR_CUDA_CHECK(cudaMemcpyToSymbol(g_attn_trace, &d_trace, sizeof(d_trace)));
     return MHMR_OK;
   }
-  static int tok = -1;  // MHMR_ATTN_TOKEN: 1 / 2 = named-barrier MUFU token, handed on after 112 / 124 exponentials
-  if (tok < 0) {
-    const char* tk = std::getenv("MHMR_ATTN_TOKEN");
-    tok = (tk != nullptr) ? atoi(tk) : kDefaultToken;
-  }
-  if (tok == 1) return attn_launch<0, 1, 112>(a);
-  if (tok == 2) return attn_launch<0, 1, 124>(a);
   return attn_launch<0>(a);
 }
 

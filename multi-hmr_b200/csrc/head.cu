@@ -317,29 +317,42 @@ __global__ void kv_add_rows_kernel(float* __restrict__ KV, int64_t ldkv, const f
 // fp32 weights streamed once per chunk of 8 persons (from L2 after the first chunk).  The input rows are
 // either fp32 rows of `x` or fp16 rows `x16[rowidx[p], :]` gathered from a token matrix (central-stream
 // refinement: rows of the attention output of the backbone's bulk pass).
-// grid = (ceil(Nout / cols), ceil(max_persons / 8)), block = 256.
+//   grid = (ceil(Nout / (8 CPW)), ceil(max_persons / 8)), block = 256: 8 warps x CPW output columns each.
+//   The 8 input rows are staged K-tile by K-tile (1024 floats per person, 32 KB static smem, 128-bit loads, LayerNorm
+//   applied on the way in from per-row statistics computed once) so that several CTAs share an SM whatever K is;
+//   every staged x value is used for CPW columns; the 8 CPW partial sums per lane are reduced with a butterfly
+//   (31 shuffles for 32 values) that leaves lane (column, person) with its total.
+// (r02: the first version staged whole rows with scalar loads in every CTA and used one column per warp: 25-37 us per
+// launch for 4-16 MB of weights; 90 such launches per forward.)
 // ----------------------------------------------------------------------------------------------
 constexpr int kSkinnyPT = 8;
+constexpr int kSkinnyKT = 1024;
 
+template <int CPW>
 __global__ void __launch_bounds__(256)
 skinny_linear_kernel(const float* __restrict__ x, int ldx, const __half* __restrict__ x16, int64_t ldx16,
                      const int* __restrict__ rowidx, const int* __restrict__ count, int K,
                      const float* __restrict__ W, int ldw, const float* __restrict__ bias, int Nout,
                      const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps, int act,
                      const float* __restrict__ gamma, const float* __restrict__ resid, int ldr,
-                     float* __restrict__ out, int ldo, int cols) {
-  extern __shared__ float xs[];  // [kSkinnyPT][Kp], Kp = K rounded up to 4
+                     float* __restrict__ out, int ldo) {
+  __shared__ __align__(16) float xs[kSkinnyPT][kSkinnyKT];
+  __shared__ float stats[kSkinnyPT][2];
+  constexpr int COLS = 8 * CPW;
   const int Kp = (K + 3) & ~3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_base = blockIdx.x * COLS + warp * CPW;
   // Programmatic dependent launch: the weights do not depend on the preceding kernel, so this CTA's weight rows are
   // pulled into L2 while that kernel drains; everything it produced (count, activations) is read after the wait.
   griddep_launch_dependents();
   if (blockIdx.y == 0) {
-    for (int c = warp; c < cols; c += 8) {
-      const int n = blockIdx.x * cols + c;
-      if (n >= Nout) break;
-      const char* wr = reinterpret_cast<const char*>(W + static_cast<int64_t>(n) * ldw);
-      for (int b = lane * 128; b < Kp * 4; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(wr + b));
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+      const int n = n_base + c;
+      if (n < Nout) {
+        const char* wr = reinterpret_cast<const char*>(W + static_cast<int64_t>(n) * ldw);
+        for (int b = lane * 128; b < Kp * 4; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(wr + b));
+      }
     }
   }
   griddep_wait();
@@ -348,67 +361,123 @@ skinny_linear_kernel(const float* __restrict__ x, int ldx, const __half* __restr
   if (p0 >= P) return;
   const int np = min(kSkinnyPT, P - p0);
 
-  // stage (and optionally LayerNorm) one person row per warp
-  {
-    float* dst = xs + warp * Kp;
+  // LayerNorm statistics of the (fp32) input rows: one warp per person, two passes over the row
+  if (ln_g != nullptr) {
     if (warp < np) {
-      float s = 0.f;
-      if (x16 != nullptr) {
-        const __half* src = x16 + static_cast<int64_t>(rowidx[p0 + warp]) * ldx16;
-        for (int k = lane; k < Kp; k += 32) {
-          const float v = (k < K) ? __half2float(src[k]) : 0.f;
-          dst[k] = v;
-          s += v;
-        }
-      } else {
-        const float* src = x + static_cast<int64_t>(p0 + warp) * ldx;
-        for (int k = lane; k < Kp; k += 32) {
-          const float v = (k < K) ? src[k] : 0.f;
-          dst[k] = v;
-          s += v;
-        }
-      }
-      if (ln_g != nullptr) {
-        const float mean = warp_sum(s) / K;
-        float q = 0.f;
-        for (int k = lane; k < K; k += 32) { const float d = dst[k] - mean; q += d * d; }
-        const float rstd = rsqrtf(warp_sum(q) / K + ln_eps);
-        for (int k = lane; k < K; k += 32) dst[k] = (dst[k] - mean) * rstd * ln_g[k] + ln_b[k];
-      }
-    } else {
-      for (int k = lane; k < Kp; k += 32) dst[k] = 0.f;
+      const float* src = x + static_cast<int64_t>(p0 + warp) * ldx;
+      float sum = 0.f;
+      for (int k = lane; k < K; k += 32) sum += src[k];
+      const float mean = warp_sum(sum) / K;
+      float q = 0.f;
+      for (int k = lane; k < K; k += 32) { const float d = src[k] - mean; q += d * d; }
+      const float rstd = rsqrtf(warp_sum(q) / K + ln_eps);
+      if (lane == 0) { stats[warp][0] = mean; stats[warp][1] = rstd; }
     }
+    __syncthreads();
   }
-  __syncthreads();
 
-  for (int c = warp; c < cols; c += 8) {
-    const int n = blockIdx.x * cols + c;
-    if (n >= Nout) break;
-    const float* wr = W + static_cast<int64_t>(n) * ldw;
-    float acc[kSkinnyPT];
+  float acc[CPW][kSkinnyPT];
 #pragma unroll
-    for (int j = 0; j < kSkinnyPT; ++j) acc[j] = 0.f;
-    for (int k = lane * 4; k < Kp; k += 128) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+  for (int c = 0; c < CPW; ++c)
+#pragma unroll
+    for (int j = 0; j < kSkinnyPT; ++j) acc[c][j] = 0.f;
+  const bool vec_x = (x16 != nullptr) || ((ldx & 3) == 0);  // 128-bit loads need 16-byte aligned rows
+
+  for (int k0 = 0; k0 < Kp; k0 += kSkinnyKT) {
+    const int kt = min(kSkinnyKT, Kp - k0);  // multiple of 4
+    const int q4 = kt >> 2;
+    // ---- stage the K tile of the 8 rows (zeros for absent persons and for k >= K)
+    for (int idx = threadIdx.x; idx < kSkinnyPT * q4; idx += 256) {
+      const int j = idx / q4, q = idx - j * q4, k = k0 + 4 * q;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < np) {
+        if (x16 != nullptr) {
+          const uint2 pk = *reinterpret_cast<const uint2*>(x16 + static_cast<int64_t>(rowidx[p0 + j]) * ldx16 + k);
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&pk.x));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&pk.y));
+          v = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+          const float* src = x + static_cast<int64_t>(p0 + j) * ldx + k;
+          if (vec_x) {
+            v = *reinterpret_cast<const float4*>(src);
+          } else {
+            v.x = src[0];
+            if (k + 1 < K) v.y = src[1];
+            if (k + 2 < K) v.z = src[2];
+            if (k + 3 < K) v.w = src[3];
+          }
+        }
+        if (ln_g != nullptr) {
+          const float mean = stats[j][0], rstd = stats[j][1];
+          const float4 g = __ldg(reinterpret_cast<const float4*>(ln_g + k));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(ln_b + k));
+          v.x = (v.x - mean) * rstd * g.x + bb.x;
+          v.y = (v.y - mean) * rstd * g.y + bb.y;
+          v.z = (v.z - mean) * rstd * g.z + bb.z;
+          v.w = (v.w - mean) * rstd * g.w + bb.w;
+        }
+        if (k + 3 >= K) {  // the padding of the last group must not contribute
+          if (k + 1 >= K) v.y = 0.f;
+          if (k + 2 >= K) v.z = 0.f;
+          if (k + 3 >= K) v.w = 0.f;
+        }
+      }
+      *reinterpret_cast<float4*>(&xs[j][4 * q]) = v;
+    }
+    __syncthreads();
+    // ---- partial dot products of this warp's CPW columns with the 8 staged rows
+    for (int k = lane * 4; k < kt; k += 128) {
+      float4 w4[CPW];
+#pragma unroll
+      for (int c = 0; c < CPW; ++c) {
+        const int n = min(n_base + c, Nout - 1);
+        w4[c] = __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(n) * ldw + k0 + k));
+      }
 #pragma unroll
       for (int j = 0; j < kSkinnyPT; ++j) {
-        const float4 x4 = *reinterpret_cast<const float4*>(xs + j * Kp + k);
-        acc[j] += w4.x * x4.x + w4.y * x4.y + w4.z * x4.z + w4.w * x4.w;
+        const float4 x4 = *reinterpret_cast<const float4*>(&xs[j][k]);
+#pragma unroll
+        for (int c = 0; c < CPW; ++c)
+          acc[c][j] += w4[c].x * x4.x + w4[c].y * x4.y + w4[c].z * x4.z + w4[c].w * x4.w;
       }
     }
+    __syncthreads();
+  }
+
+  // ---- butterfly reduction: NV = 8 CPW values per lane -> lane L holds the total of value L (mod NV)
+  constexpr int NV = CPW * kSkinnyPT;
+  float a[NV];
 #pragma unroll
-    for (int j = 0; j < kSkinnyPT; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane < np) {
-      float v = 0.f;
+  for (int c = 0; c < CPW; ++c)
 #pragma unroll
-      for (int j = 0; j < kSkinnyPT; ++j) v = (lane == j) ? acc[j] : v;
-      if (bias != nullptr) v += bias[n];
-      if (act == 1) v = fmaxf(v, 0.f);
-      if (act == 2) v = gelu_erf(v);
-      if (gamma != nullptr) v *= gamma[n];
-      if (resid != nullptr) v += resid[static_cast<int64_t>(p0 + lane) * ldr + n];
-      out[static_cast<int64_t>(p0 + lane) * ldo + n] = v;
+    for (int j = 0; j < kSkinnyPT; ++j) a[c * kSkinnyPT + j] = acc[c][j];
+  if constexpr (NV < 32) {
+#pragma unroll
+    for (int o = 16; o >= NV; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+  }
+#pragma unroll
+  for (int o = (NV < 32 ? NV / 2 : 16); o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? a[i] : a[i + o];
+      const float keep = up ? a[i + o] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
     }
+  }
+  const int vi = lane & (NV - 1);
+  const int c = vi / kSkinnyPT, j = vi - c * kSkinnyPT;
+  const int n = n_base + c;
+  if (lane < NV && j < np && n < Nout) {
+    float v = a[0];
+    if (bias != nullptr) v += bias[n];
+    if (act == 1) v = fmaxf(v, 0.f);
+    if (act == 2) v = gelu_erf(v);
+    if (gamma != nullptr) v *= gamma[n];
+    if (resid != nullptr) v += resid[static_cast<int64_t>(p0 + j) * ldr + n];
+    out[static_cast<int64_t>(p0 + j) * ldo + n] = v;
   }
 }
 
@@ -717,35 +786,33 @@ int kv_add_rows(float* KV, int64_t ldkv, const float* dKV, int ncols, const int*
 int skinny_linear_ex(const float* x, int ldx, const SkinnyExtra& ex, const int* count, int max_persons, int K,
                      const float* W, int ldw, const float* bias, int Nout, const float* ln_g, const float* ln_b,
                      float ln_eps, int act, const float* resid, int ldr, float* out, int ldo, cudaStream_t st) {
-  MHMR_REQUIRE(ldw % 4 == 0 && ldw >= ((K + 3) & ~3), "skinny_linear: weight pitch must be >= K rounded to 4");
-  MHMR_REQUIRE((x != nullptr) != (ex.x16 != nullptr), "skinny_linear: exactly one of x / x16");
-  MHMR_REQUIRE(ex.x16 == nullptr || ex.rowidx != nullptr, "skinny_linear: x16 needs row indices");
   const int Kp = (K + 3) & ~3;
-  const size_t smem = static_cast<size_t>(kSkinnyPT) * Kp * sizeof(float);
-  constexpr size_t kMaxSmem = 200 * 1024;
-  static PerDeviceOnce once;
-  if (once.first()) {
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kMaxSmem)));
-  }
-  MHMR_REQUIRE(smem <= kMaxSmem, "skinny_linear: K too large");
-  // columns per CTA: 32 by default; fewer when that leaves most SMs without work (weight streaming is the cost)
-  int cols = ex.cols > 0 ? ex.cols : 32;
-  if (ex.cols <= 0) {
-    while (cols > 8 && (Nout + cols - 1) / cols < 2 * device_sm_count()) cols >>= 1;
-  }
+  MHMR_REQUIRE(ldw % 4 == 0 && ldw >= Kp, "skinny_linear: weight pitch must be >= K rounded to 4");
+  MHMR_REQUIRE((x != nullptr) != (ex.x16 != nullptr), "skinny_linear: exactly one of x / x16");
+  MHMR_REQUIRE(ex.x16 == nullptr || (ex.rowidx != nullptr && ex.ldx16 % 4 == 0 && K % 4 == 0),
+               "skinny_linear: x16 needs row indices, a pitch and K that are multiples of 4");
+  MHMR_REQUIRE(x == nullptr || (ldx % 4 != 0) || ldx >= Kp, "skinny_linear: input pitch must cover K rounded to 4");
+  MHMR_REQUIRE(ln_g == nullptr || (x != nullptr && K % 4 == 0), "skinny_linear: LayerNorm needs fp32 rows, K % 4 == 0");
+  // columns per warp: 4 (32 per CTA) by default, 2 when that leaves fewer CTAs than SMs for one 8-person chunk
+  int cpw = (ex.cols == 16) ? 2 : 4;
+  if (ex.cols <= 0 && (Nout + 31) / 32 < device_sm_count()) cpw = 2;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((Nout + cols - 1) / cols, (max_persons + kSkinnyPT - 1) / kSkinnyPT);
+  cfg.gridDim = dim3((Nout + 8 * cpw - 1) / (8 * cpw), (max_persons + kSkinnyPT - 1) / kSkinnyPT);
   cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, skinny_linear_kernel, x, ldx, ex.x16, ex.ldx16, ex.rowidx, count, K, W, ldw,
-                                     bias, Nout, ln_g, ln_b, ln_eps, act, ex.gamma, resid, ldr, out, ldo, cols));
+  if (cpw == 4) {
+    MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, skinny_linear_kernel<4>, x, ldx, ex.x16, ex.ldx16, ex.rowidx, count, K, W, ldw,
+                                       bias, Nout, ln_g, ln_b, ln_eps, act, ex.gamma, resid, ldr, out, ldo));
+  } else {
+    MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, skinny_linear_kernel<2>, x, ldx, ex.x16, ex.ldx16, ex.rowidx, count, K, W, ldw,
+                                       bias, Nout, ln_g, ln_b, ln_eps, act, ex.gamma, resid, ldr, out, ldo));
+  }
   return MHMR_OK;
 }
 
@@ -753,7 +820,6 @@ int skinny_linear(const float* x, int ldx, const int* count, int max_persons, in
                   const float* bias, int Nout, const float* ln_g, const float* ln_b, float ln_eps, int act,
                   const float* resid, int ldr, float* out, int ldo, cudaStream_t st) {
   SkinnyExtra ex;
-  ex.cols = 32;
   return skinny_linear_ex(x, ldx, ex, count, max_persons, K, W, ldw, bias, Nout, ln_g, ln_b, ln_eps, act, resid, ldr,
                           out, ldo, st);
 }
