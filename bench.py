@@ -475,25 +475,38 @@ def usable_cpus() -> dict:
 
 
 def pick_cpu_threads(info: dict) -> int:
-    """Short GEMM probe (the forward is GEMM-dominated) over {usable, usable/2, physical cores}: keep the fastest."""
+    """Short probe over {usable, usable/2, physical cores}: one ViT block of the workload's width on one image's
+    tokens (Linear + attention + GELU — what the forward is made of; a bare GEMM probe picked 8 of 16 threads on one box
+    and 16 on another).  Keeps the fastest; ties within 5 % go to the larger count."""
     import torch
+
+    from oracle import dinov2_ref
 
     cands = {info["usable"], max(1, info["usable"] // 2)}
     if info.get("physical"):
         cands.add(max(1, min(info["usable"], info["physical"])))
-    a, b = torch.randn(4097, 1024), torch.randn(1024, 4096)
+    D, heads, T = 1024, 16, (WORKLOAD["img_size"] // 14) ** 2 + 1
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g) * 0.02
+    sd = {"b.norm1.weight": torch.ones(D), "b.norm1.bias": torch.zeros(D), "b.norm2.weight": torch.ones(D),
+          "b.norm2.bias": torch.zeros(D), "b.attn.qkv.weight": r(3 * D, D), "b.attn.qkv.bias": r(3 * D),
+          "b.attn.proj.weight": r(D, D), "b.attn.proj.bias": r(D), "b.ls1.gamma": torch.ones(D),
+          "b.ls2.gamma": torch.ones(D), "b.mlp.fc1.weight": r(4 * D, D), "b.mlp.fc1.bias": r(4 * D),
+          "b.mlp.fc2.weight": r(D, 4 * D), "b.mlp.fc2.bias": r(D)}
+    xx = torch.randn(1, T, D, generator=g)
     best, best_t, probe = None, None, {}
     for n in sorted(cands, reverse=True):
         torch.set_num_threads(n)
-        torch.mm(a, b)
-        t0 = time.perf_counter()
-        for _ in range(4):
-            torch.mm(a, b)
-        dt = (time.perf_counter() - t0) / 4
-        probe[n] = round(2 * 4097 * 1024 * 4096 / dt / 1e9, 1)  # GFLOP/s
-        if best_t is None or dt < best_t:
+        with torch.no_grad():
+            dinov2_ref.vit_block(xx, sd, "b.", heads)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                dinov2_ref.vit_block(xx, sd, "b.", heads)
+            dt = (time.perf_counter() - t0) / 2
+        probe[n] = round(dt * 1e3, 1)  # ms per ViT block
+        if best_t is None or dt < 0.95 * best_t:
             best, best_t = n, dt
-    info["probe_gflops_by_threads"] = probe
+    info["probe_ms_per_vit_block_by_threads"] = probe
     torch.set_num_threads(best)
     return best
 
