@@ -87,7 +87,9 @@ struct mhmr_engine {
   int *det = nullptr, *count = nullptr, *img_off = nullptr;
   // central-stream refinement: token rows, input patches, residual streams and MLP hidden of the detected persons
   int* r_rowidx = nullptr;
-  float *r_patch = nullptr, *r_x = nullptr, *r_h = nullptr;
+  float *r_patch = nullptr, *r_x = nullptr, *r_h = nullptr, *r_term = nullptr;
+  RefineLayer* r_layers = nullptr;   // device array [depth]
+  unsigned int* r_barrier = nullptr;
   const float* Wpatch32 = nullptr;
   float *zc = nullptr, *query = nullptr, *vals = nullptr, *dKV = nullptr, *offh = nullptr, *xa = nullptr,
         *qkvp = nullptr, *att = nullptr, *qca = nullptr, *ffh = nullptr, *dec = nullptr, *K_det = nullptr,
@@ -335,6 +337,16 @@ int finalize_head(mhmr_engine* e, cudaStream_t st) {
     TRY(e->alloc(&e->r_patch, static_cast<size_t>(Pm) * 592));
     TRY(e->alloc(&e->r_x, static_cast<size_t>(Pm) * D));
     TRY(e->alloc(&e->r_h, static_cast<size_t>(Pm) * 4 * D));
+    TRY(e->alloc(&e->r_term, static_cast<size_t>(e->depth) * Pm * D));
+    TRY(e->alloc(&e->r_barrier, 4));
+    std::vector<RefineLayer> rl(e->depth);
+    for (int l = 0; l < e->depth; ++l) {
+      const VitLayer& L = e->vit[l];
+      rl[l] = RefineLayer{L.O16, L.Wproj32, L.bproj, L.ls1, L.ln2_g, L.ln2_b, L.Wfc1_32, L.bfc1, L.Wfc2_32, L.bfc2, L.ls2};
+    }
+    TRY(e->alloc(&e->r_layers, rl.size()));
+    MHMR_CUDA_CHECK(cudaMemcpyAsync(e->r_layers, rl.data(), rl.size() * sizeof(RefineLayer), cudaMemcpyHostToDevice, st));
+    MHMR_CUDA_CHECK(cudaStreamSynchronize(st));  // rl lives on this stack frame
   }
   return MHMR_OK;
 }
@@ -452,7 +464,9 @@ int vit_forward(mhmr_engine* e, const ImgSrc& x, int B, float* z_out, cudaStream
 // tools/precision_study.py).  Those few rows are recomputed here in fp32 with the fp32 master weights:
 //   x = patch-embed(pixels) + pos;  per block: x += ls1 * (Wproj . O16[row] + b);  x += ls2 * MLP(LN2(x))
 // where O16[row] is the attention output of the bulk pass for that token (kept per layer).  The final norm is
-// applied by person_gather.  Same arithmetic as dinov2 Block.forward (reached from blocks/dinov2.py:25).
+// applied by person_gather.  Same arithmetic as dinov2 Block.forward (reached from blocks/dinov2.py:25).  Four
+// launches: patches / row indices, patch embedding, every projection term at once, the MLP chain of all blocks in one
+// persistent cooperative kernel (refine.cu).
 int refine_streams(mhmr_engine* e, const ImgSrc& x, const int* det_b, const int* det_y, const int* det_x,
                    const int* count, cudaStream_t st) {
   const int D = e->D, Pm = e->cfg.max_persons;
@@ -461,19 +475,8 @@ int refine_streams(mhmr_engine* e, const ImgSrc& x, const int* det_b, const int*
   SkinnyExtra none;
   LAUNCH(MHMR_CAT_REFINE, skinny_linear_ex(e->r_patch, 592, none, count, Pm, 588, e->Wpatch32, 588, nullptr, D, nullptr,
                                            nullptr, 0.f, 0, e->r_x, D, e->r_x, D, st));
-  for (int l = 0; l < e->depth; ++l) {
-    VitLayer& L = e->vit[l];
-    SkinnyExtra po;
-    po.x16 = L.O16; po.ldx16 = D; po.rowidx = e->r_rowidx; po.gamma = L.ls1;
-    LAUNCH(MHMR_CAT_REFINE, skinny_linear_ex(nullptr, 0, po, count, Pm, D, L.Wproj32, D, L.bproj, D, nullptr, nullptr, 0.f,
-                                             0, e->r_x, D, e->r_x, D, st));
-    LAUNCH(MHMR_CAT_REFINE, skinny_linear_ex(e->r_x, D, none, count, Pm, D, L.Wfc1_32, D, L.bfc1, 4 * D, L.ln2_g, L.ln2_b,
-                                             1e-6f, 2, nullptr, 0, e->r_h, 4 * D, st));
-    SkinnyExtra f2;
-    f2.gamma = L.ls2;
-    LAUNCH(MHMR_CAT_REFINE, skinny_linear_ex(e->r_h, 4 * D, f2, count, Pm, 4 * D, L.Wfc2_32, 4 * D, L.bfc2, D, nullptr,
-                                             nullptr, 0.f, 0, e->r_x, D, e->r_x, D, st));
-  }
+  LAUNCH(MHMR_CAT_REFINE, refine_proj_terms(e->r_layers, e->depth, e->r_rowidx, count, D, Pm, e->r_term, st));
+  LAUNCH(MHMR_CAT_REFINE, refine_mlp_chain(e->r_layers, e->depth, count, D, Pm, e->r_term, e->r_x, e->r_h, e->r_barrier, st));
   return MHMR_OK;
 }
 

@@ -63,6 +63,17 @@ struct SkinnyExtra {
 int skinny_linear_ex(const float* x, int ldx, const SkinnyExtra& ex, const int* count, int max_persons, int K,
                      const float* W, int ldw, const float* bias, int Nout, const float* ln_g, const float* ln_b,
                      float ln_eps, int act, const float* resid, int ldr, float* out, int ldo, cudaStream_t st);
+// ---- refine.cu: central-stream refinement -----------------------------------------
+struct RefineLayer {
+  const __half* O16;  // this block's attention output of the bulk pass [B*T, D]
+  const float *Wproj, *bproj, *ls1, *ln2_g, *ln2_b, *Wfc1, *bfc1, *Wfc2, *bfc2, *ls2;  // fp32 masters
+};
+// term[l][p][:] = ls1_l * (W_proj_l . O16_l[rowidx[p], :] + b_proj_l) for every block l: ONE launch
+int refine_proj_terms(const RefineLayer* layers, int depth, const int* rowidx, const int* count, int D,
+                      int max_persons, float* term, cudaStream_t st);
+// x[p][:] <- for every block: (x + term_l) + ls2_l * MLP_l(LN2_l(x + term_l)): ONE persistent cooperative launch
+int refine_mlp_chain(const RefineLayer* layers, int depth, const int* count, int D, int max_persons, const float* term,
+                     float* x, float* h, unsigned int* barrier, cudaStream_t st);
 int hph_self_attn(const float* qkv, int ld, const int* det_b, const int* img_off, const int* count,
                   int max_persons, int heads, float* out, int ldo, cudaStream_t st);
 int hph_cross_attn(const float* q, int ldq, const float* KV, int64_t ldkv, int k_col, int v_col,

@@ -1,0 +1,288 @@
+// Central-stream refinement: the residual streams of the detected tokens recomputed in fp32.
+//
+//   x = W_patch . pixels + (pos + bias)                                   (refine_prepare + one skinny linear, head.cu)
+//   per block l:  x += ls1_l * (W_proj_l . O16_l[row] + b_proj_l)         (A)  depends on the bulk pass only
+//                 x += ls2_l * (W_fc2_l . gelu(W_fc1_l . LN2_l(x) + b_fc1_l) + b_fc2_l)        (B)
+// Same arithmetic as dinov2 Block.forward (reached from reference blocks/dinov2.py:25) for the few rows that the
+// per-person outputs are sensitive to.
+//
+// x and h are written and re-read across grid barriers by different SMs: they are read with ld.global.cg (L2), never
+// through the (incoherent) L1.
+//
+// The first version launched three skinny linears per block: 74 dependent launches of ~20 us (latency chains, not
+// bandwidth: 2.1 ms of a 39.5 ms step).  Here
+//   * every term (A) is computed up front by ONE batched launch (blockIdx.z = block): they only need the attention
+//     outputs O16_l of the bulk pass, not x;
+//   * the chain (B) of all blocks runs in ONE persistent cooperative kernel: each CTA owns a fixed slice of the fc1 /
+//     fc2 output columns, stages the (few) person rows in shared memory, and a grid barrier separates the two phases
+//     of a block; the next phase's weight slice is pulled into L2 before the barrier.  Column ownership is fixed, so
+//     the result does not depend on scheduling (bit-reproducible).
+#include "kernels.cuh"
+
+namespace mhmr {
+
+namespace {
+
+constexpr int kPT = 8;       // persons per pass
+constexpr int kKT = 1024;    // K tile staged per person (floats)
+
+__device__ __forceinline__ void prefetch_l2_rows(const float* W, int64_t ldw, int n0, int ncols, int Nout, int Kp, int warp,
+                                                 int lane) {
+  for (int c = warp; c < ncols; c += 8) {
+    const int n = n0 + c;
+    if (n >= Nout) break;
+    const char* wr = reinterpret_cast<const char*>(W + static_cast<int64_t>(n) * ldw);
+    for (int b = lane * 128; b < Kp * 4; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(wr + b));
+  }
+}
+
+// Butterfly reduction of NV = CPW * 8 values per lane: lane L ends with the total of value (L mod NV) in a[0].
+template <int NV>
+__device__ __forceinline__ void butterfly(float (&a)[NV], int lane) {
+  if constexpr (NV < 32) {
+#pragma unroll
+    for (int o = 16; o >= NV; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+  }
+#pragma unroll
+  for (int o = (NV < 32 ? NV / 2 : 16); o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? a[i] : a[i + o];
+      const float keep = up ? a[i + o] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+}
+
+// acc[c][j] += W[n_base + c, k0 : k0 + kt] . xs[j][0 : kt]   for this warp's CPW columns and the 8 staged rows
+template <int CPW>
+__device__ __forceinline__ void tile_dot(const float* __restrict__ W, int64_t ldw, int n_base, int Nout, int k0, int kt,
+                                         const float (*xs)[kKT], int lane, float (&acc)[CPW][kPT]) {
+  for (int k = lane * 4; k < kt; k += 128) {
+    float4 w4[CPW];
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+      const int n = min(n_base + c, Nout - 1);
+      w4[c] = __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(n) * ldw + k0 + k));
+    }
+#pragma unroll
+    for (int j = 0; j < kPT; ++j) {
+      const float4 x4 = *reinterpret_cast<const float4*>(&xs[j][k]);
+#pragma unroll
+      for (int c = 0; c < CPW; ++c) acc[c][j] += w4[c].x * x4.x + w4[c].y * x4.y + w4[c].z * x4.z + w4[c].w * x4.w;
+    }
+  }
+}
+
+// ---- (A) all projection terms at once: term[l][p][n] = ls1_l[n] * (W_proj_l[n, :] . O16_l[row_p, :] + b_proj_l[n])
+__global__ void __launch_bounds__(256)
+refine_proj_terms_kernel(const RefineLayer* __restrict__ layers, const int* __restrict__ rowidx,
+                         const int* __restrict__ count, int D, int max_persons, float* __restrict__ term) {
+  __shared__ __align__(16) float xs[kPT][kKT];
+  constexpr int CPW = 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const RefineLayer L = layers[blockIdx.z];
+  const int n_base = blockIdx.x * (8 * CPW) + warp * CPW;
+  griddep_launch_dependents();
+  if (blockIdx.y == 0) prefetch_l2_rows(L.Wproj, D, blockIdx.x * 8 * CPW, 8 * CPW, D, D, warp, lane);
+  griddep_wait();
+  const int P = *count;
+  const int p0 = blockIdx.y * kPT;
+  if (p0 >= P) return;
+  const int np = min(kPT, P - p0);
+  float acc[CPW][kPT];
+#pragma unroll
+  for (int c = 0; c < CPW; ++c)
+#pragma unroll
+    for (int j = 0; j < kPT; ++j) acc[c][j] = 0.f;
+  for (int k0 = 0; k0 < D; k0 += kKT) {
+    const int kt = min(kKT, D - k0), q4 = kt >> 2;
+    for (int idx = threadIdx.x; idx < kPT * q4; idx += 256) {
+      const int j = idx / q4, q = idx - j * q4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < np) {
+        const uint2 pk = *reinterpret_cast<const uint2*>(L.O16 + static_cast<int64_t>(rowidx[p0 + j]) * D + k0 + 4 * q);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&pk.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&pk.y));
+        v = make_float4(a.x, a.y, b.x, b.y);
+      }
+      *reinterpret_cast<float4*>(&xs[j][4 * q]) = v;
+    }
+    __syncthreads();
+    tile_dot<CPW>(L.Wproj, D, n_base, D, k0, kt, xs, lane, acc);
+    __syncthreads();
+  }
+  float a[CPW * kPT];
+#pragma unroll
+  for (int c = 0; c < CPW; ++c)
+#pragma unroll
+    for (int j = 0; j < kPT; ++j) a[c * kPT + j] = acc[c][j];
+  butterfly<CPW * kPT>(a, lane);
+  const int vi = lane & (CPW * kPT - 1), c = vi / kPT, j = vi - c * kPT, n = n_base + c;
+  if (lane < CPW * kPT && j < np && n < D)
+    term[(static_cast<int64_t>(blockIdx.z) * max_persons + p0 + j) * D + n] = L.ls1[n] * (a[0] + L.bproj[n]);
+}
+
+// ---- (B) the MLP chain of every block in one persistent cooperative kernel
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int spins = 0;
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+      if (++spins > (1u << 30)) __trap();  // a protocol bug must surface as an error, never as a hung GPU
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+refine_mlp_chain_kernel(const RefineLayer* __restrict__ layers, int depth, const int* __restrict__ count, int D,
+                        int max_persons, const float* __restrict__ term, float* x, float* h, unsigned int* barrier) {
+  __shared__ __align__(16) float xs[kPT][kKT];
+  __shared__ float stats[kPT][2];
+  constexpr int CPW1 = 4, CPW2 = 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, H = 4 * D;
+  // fixed column ownership: fc1 (4D outputs) in slices of cols1 = 8 * CPW1 per CTA (strided over the grid), fc2 (D
+  // outputs) in slices of 8 per CTA
+  const int P = *count;
+  unsigned int phase = 0;
+  for (int l = 0; l < depth; ++l) {
+    const RefineLayer L = layers[l];
+    const float* tl = term + static_cast<int64_t>(l) * max_persons * D;
+    // ---------------- phase 1: h = gelu(W_fc1 . LN2(x + term_l) + b_fc1)
+    for (int p0 = 0; p0 < P; p0 += kPT) {
+      const int np = min(kPT, P - p0);
+      if (warp < np) {  // LayerNorm statistics of row p0 + warp (eps 1e-6), two passes
+        const float* xr = x + static_cast<int64_t>(p0 + warp) * D;
+        const float* tr = tl + static_cast<int64_t>(p0 + warp) * D;
+        float s = 0.f;
+        for (int k = lane; k < D; k += 32) s += __ldcg(xr + k) + tr[k];
+        const float mean = warp_sum(s) / D;
+        float q = 0.f;
+        for (int k = lane; k < D; k += 32) { const float d = (__ldcg(xr + k) + tr[k]) - mean; q += d * d; }
+        const float rstd = rsqrtf(warp_sum(q) / D + 1e-6f);
+        if (lane == 0) { stats[warp][0] = mean; stats[warp][1] = rstd; }
+      }
+      __syncthreads();
+      for (int cb = blockIdx.x; cb * (8 * CPW1) < H; cb += G) {
+        const int n_base = cb * (8 * CPW1) + warp * CPW1;
+        float acc[CPW1][kPT];
+#pragma unroll
+        for (int c = 0; c < CPW1; ++c)
+#pragma unroll
+          for (int j = 0; j < kPT; ++j) acc[c][j] = 0.f;
+        for (int k0 = 0; k0 < D; k0 += kKT) {
+          const int kt = min(kKT, D - k0), q4 = kt >> 2;
+          for (int idx = threadIdx.x; idx < kPT * q4; idx += 256) {
+            const int j = idx / q4, q = idx - j * q4, k = k0 + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < np) {
+              const float4 a = __ldcg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(p0 + j) * D + k));
+              const float4 t = *reinterpret_cast<const float4*>(tl + static_cast<int64_t>(p0 + j) * D + k);
+              const float4 g = __ldg(reinterpret_cast<const float4*>(L.ln2_g + k));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(L.ln2_b + k));
+              const float mean = stats[j][0], rstd = stats[j][1];
+              v.x = ((a.x + t.x) - mean) * rstd * g.x + b.x;
+              v.y = ((a.y + t.y) - mean) * rstd * g.y + b.y;
+              v.z = ((a.z + t.z) - mean) * rstd * g.z + b.z;
+              v.w = ((a.w + t.w) - mean) * rstd * g.w + b.w;
+            }
+            *reinterpret_cast<float4*>(&xs[j][4 * q]) = v;
+          }
+          __syncthreads();
+          tile_dot<CPW1>(L.Wfc1, D, n_base, H, k0, kt, xs, lane, acc);
+          __syncthreads();
+        }
+        float a[CPW1 * kPT];
+#pragma unroll
+        for (int c = 0; c < CPW1; ++c)
+#pragma unroll
+          for (int j = 0; j < kPT; ++j) a[c * kPT + j] = acc[c][j];
+        butterfly<CPW1 * kPT>(a, lane);
+        const int c = lane / kPT, j = lane - c * kPT, n = n_base + c;
+        if (j < np && n < H) h[static_cast<int64_t>(p0 + j) * H + n] = gelu_erf(a[0] + L.bfc1[n]);
+      }
+      __syncthreads();  // stats / xs are reused by the next chunk of persons
+    }
+    for (int cb = blockIdx.x; cb * 8 < D; cb += G) prefetch_l2_rows(L.Wfc2, H, cb * 8, 8, D, H, warp, lane);
+    grid_barrier(barrier, ++phase * G);
+    // ---------------- phase 2: x = (x + term_l) + ls2 * (W_fc2 . h + b_fc2)
+    for (int p0 = 0; p0 < P; p0 += kPT) {
+      const int np = min(kPT, P - p0);
+      for (int cb = blockIdx.x; cb * 8 < D; cb += G) {
+        const int n_base = cb * 8 + warp * CPW2;
+        float acc[CPW2][kPT];
+#pragma unroll
+        for (int j = 0; j < kPT; ++j) acc[0][j] = 0.f;
+        for (int k0 = 0; k0 < H; k0 += kKT) {
+          const int kt = min(kKT, H - k0), q4 = kt >> 2;
+          for (int idx = threadIdx.x; idx < kPT * q4; idx += 256) {
+            const int j = idx / q4, q = idx - j * q4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < np) v = __ldcg(reinterpret_cast<const float4*>(h + static_cast<int64_t>(p0 + j) * H + k0 + 4 * q));
+            *reinterpret_cast<float4*>(&xs[j][4 * q]) = v;
+          }
+          __syncthreads();
+          tile_dot<CPW2>(L.Wfc2, H, n_base, D, k0, kt, xs, lane, acc);
+          __syncthreads();
+        }
+        float a[CPW2 * kPT];
+#pragma unroll
+        for (int j = 0; j < kPT; ++j) a[j] = acc[0][j];
+        butterfly<CPW2 * kPT>(a, lane);
+        const int j = lane & (kPT - 1), n = n_base;
+        if (lane < kPT && j < np && n < D) {
+          const int64_t o = static_cast<int64_t>(p0 + j) * D + n;
+          x[o] = (__ldcg(x + o) + tl[o]) + L.ls2[n] * (a[0] + L.bfc2[n]);
+        }
+      }
+    }
+    if (l + 1 < depth) {
+      const RefineLayer Ln = layers[l + 1];
+      for (int cb = blockIdx.x; cb * (8 * CPW1) < H; cb += G) prefetch_l2_rows(Ln.Wfc1, D, cb * 8 * CPW1, 8 * CPW1, H, D, warp, lane);
+    }
+    grid_barrier(barrier, ++phase * G);
+  }
+}
+
+}  // namespace
+
+int refine_proj_terms(const RefineLayer* layers, int depth, const int* rowidx, const int* count, int D,
+                      int max_persons, float* term, cudaStream_t st) {
+  MHMR_REQUIRE(D % 4 == 0, "refine: D must be a multiple of 4");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((D + 15) / 16, (max_persons + kPT - 1) / kPT, depth);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, refine_proj_terms_kernel, layers, rowidx, count, D, max_persons, term));
+  return MHMR_OK;
+}
+
+int refine_mlp_chain(const RefineLayer* layers, int depth, const int* count, int D, int max_persons, const float* term,
+                     float* x, float* h, unsigned int* barrier, cudaStream_t st) {
+  MHMR_REQUIRE(D % 4 == 0, "refine: D must be a multiple of 4");
+  MHMR_CUDA_CHECK(cudaMemsetAsync(barrier, 0, sizeof(unsigned int), st));
+  // one CTA per 32 fc1 columns, at most one per SM: every CTA is resident (cooperative launch), so the grid barrier
+  // cannot deadlock
+  int grid = (4 * D + 31) / 32;
+  if (grid > device_sm_count()) grid = device_sm_count();
+  void* args[] = {(void*)&layers, (void*)&depth, (void*)&count, (void*)&D, (void*)&max_persons,
+                  (void*)&term,   (void*)&x,     (void*)&h,     (void*)&barrier};
+  MHMR_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(refine_mlp_chain_kernel), dim3(grid), dim3(256),
+                                              args, 0, st));
+  return MHMR_OK;
+}
+
+}  // namespace mhmr
