@@ -67,7 +67,6 @@ constexpr int kTileBytes = 128 * kHeadDim * 2;  // 16 KB: Q, K or V tile
 constexpr int kBarrierBytes = 512;              // mbarriers + the TMEM slot
 constexpr int kStagesK = 4, kStagesV = 4;
 constexpr int kQTiles = 4;    // two items x two query tiles
-constexpr int kDefaultUseV1 = 0;     // MHMR_ATTN_V1=1 selects the round-1 kernel (A/B timing)
 constexpr int kDefaultSimtTail = -1; // MHMR_ATTN_TAIL: 1 / 0 force the SIMT tail rows on / off, -1 = decide per problem
 constexpr int kPassAt = 112;  // exponentials issued before the MUFU token is handed on (measured optimum)
 
@@ -734,14 +733,6 @@ int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ld
   MHMR_REQUIRE(D % kHeadDim == 0, "attention: embed dim must be a multiple of 64");
   MHMR_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0, "attention: row pitches must be multiples of 8");
   MHMR_REQUIRE(B > 0 && T > 0, "attention: empty problem");
-  {  // A/B against the round-1 kernel (one CTA per query-tile pair); MHMR_ATTN_V1=0 / 1 overrides the default
-    static int use_v1 = -1;
-    if (use_v1 < 0) {
-      const char* ve = std::getenv("MHMR_ATTN_V1");
-      use_v1 = (ve != nullptr) ? atoi(ve) : kDefaultUseV1;
-    }
-    if (use_v1) return attention_forward_v1(qkv, ld_qkv, out, ldo, B, T, D, stream);
-  }
   AttnArgs a;
   int rc = make_tmap_2d(&a.tm, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<uint64_t>(B) * T,
                         3ull * D, ld_qkv * 2, 128, 64, true);

@@ -7,8 +7,6 @@ namespace mhmr {
 // ---- attn_tc.cu ------------------------------------------------------------------------------
 int attention_forward(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ldo, int B, int T, int D,
                       cudaStream_t stream);
-int attention_forward_v1(const __half* qkv, int64_t ld_qkv, __half* out, int64_t ldo, int B, int T, int D,
-                         cudaStream_t stream);  // attn_tc_v1.cu: round-1 kernel, A/B timing only
 
 // ---- vit_misc.cu -----------------------------------------------------------------------------
 int im2col_patch14(const float* x, __half* A, int B, int S, int ldA, cudaStream_t stream);
