@@ -141,16 +141,70 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
+// One linear layer phase for the 8 staged rows xs[8][K]: this CTA's columns [n0, n0 + 4 * ngroups), K split across the
+// 8 warps (each warp a contiguous K slice, every lane 4 consecutive k per 128-wide step), 4 columns at a time; the
+// per-warp partial sums go through shared memory (red[warp][group * 32 + lane]) and are added up by one thread per
+// (column, person).  Many independent weight loads in flight per lane, one pass over the staged rows per group.
+template <typename Epi>
+__device__ __forceinline__ void cta_linear(const float* __restrict__ W, int64_t ldw, int Nout, int K, int n0, int ngroups,
+                                           const float* xs, int ldxs, float* red, int warp, int lane, Epi epi) {
+  const int slice = ((K / 8) + 3) & ~3;           // K slice of a warp (multiple of 4)
+  const int kbeg = warp * slice, kend = min(K, kbeg + slice);
+  for (int g = 0; g < ngroups; ++g) {
+    const int n_base = n0 + 4 * g;
+    float acc[4][kPT];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < kPT; ++j) acc[c][j] = 0.f;
+    for (int k = kbeg + lane * 4; k < kend; k += 128) {
+      float4 w4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int n = min(n_base + c, Nout - 1);
+        w4[c] = __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(n) * ldw + k));
+      }
+#pragma unroll
+      for (int j = 0; j < kPT; ++j) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xs + j * ldxs + k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c][j] += w4[c].x * x4.x + w4[c].y * x4.y + w4[c].z * x4.z + w4[c].w * x4.w;
+      }
+    }
+    float a[4 * kPT];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < kPT; ++j) a[c * kPT + j] = acc[c][j];
+    butterfly<4 * kPT>(a, lane);
+    red[warp * 256 + g * 32 + lane] = a[0];   // value index lane = (column c = lane / 8, person j = lane % 8)
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < ngroups * 32) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w * 256 + t];
+    const int g = t >> 5, c = (t & 31) / kPT, j = t & (kPT - 1);
+    const int n = n0 + 4 * g + c;
+    if (n < Nout) epi(n, j, v);
+  }
+  __syncthreads();
+}
+
+// ---- (B) the MLP chain of every block in one persistent cooperative kernel
 __global__ void __launch_bounds__(256)
 refine_mlp_chain_kernel(const RefineLayer* __restrict__ layers, int depth, const int* __restrict__ count, int D,
                         int max_persons, const float* __restrict__ term, float* x, float* h, unsigned int* barrier) {
-  __shared__ __align__(16) float xs[kPT][kKT];
+  extern __shared__ __align__(16) float dyn[];
+  const int H = 4 * D;
+  float* xs = dyn;                 // [8][H] (phase 2) / [8][D] (phase 1)
+  float* red = dyn + kPT * H;      // [8 warps][256]
   __shared__ float stats[kPT][2];
-  constexpr int CPW1 = 4, CPW2 = 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = gridDim.x, H = 4 * D;
-  // fixed column ownership: fc1 (4D outputs) in slices of cols1 = 8 * CPW1 per CTA (strided over the grid), fc2 (D
-  // outputs) in slices of 8 per CTA
+  const int G = gridDim.x;
+  // fixed column ownership: fc1 (4D outputs) in slices of 32 per CTA, fc2 (D outputs) in slices of 8 per CTA,
+  // both strided over the grid
   const int P = *count;
   unsigned int phase = 0;
   for (int l = 0; l < depth; ++l) {
@@ -159,94 +213,73 @@ refine_mlp_chain_kernel(const RefineLayer* __restrict__ layers, int depth, const
     // ---------------- phase 1: h = gelu(W_fc1 . LN2(x + term_l) + b_fc1)
     for (int p0 = 0; p0 < P; p0 += kPT) {
       const int np = min(kPT, P - p0);
-      if (warp < np) {  // LayerNorm statistics of row p0 + warp (eps 1e-6), two passes
-        const float* xr = x + static_cast<int64_t>(p0 + warp) * D;
-        const float* tr = tl + static_cast<int64_t>(p0 + warp) * D;
+      for (int idx = threadIdx.x; idx < kPT * (D >> 2); idx += 256) {   // raw rows x + term
+        const int j = idx / (D >> 2), k = 4 * (idx - j * (D >> 2));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < np) {
+          const float4 a = __ldcg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(p0 + j) * D + k));
+          const float4 t = *reinterpret_cast<const float4*>(tl + static_cast<int64_t>(p0 + j) * D + k);
+          v = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+        }
+        *reinterpret_cast<float4*>(xs + j * D + k) = v;
+      }
+      __syncthreads();
+      if (warp < np) {  // LayerNorm statistics (eps 1e-6) of row `warp`, two passes over shared memory
+        const float* r = xs + warp * D;
         float s = 0.f;
-        for (int k = lane; k < D; k += 32) s += __ldcg(xr + k) + tr[k];
+        for (int k = lane; k < D; k += 32) s += r[k];
         const float mean = warp_sum(s) / D;
         float q = 0.f;
-        for (int k = lane; k < D; k += 32) { const float d = (__ldcg(xr + k) + tr[k]) - mean; q += d * d; }
+        for (int k = lane; k < D; k += 32) { const float d = r[k] - mean; q += d * d; }
         const float rstd = rsqrtf(warp_sum(q) / D + 1e-6f);
         if (lane == 0) { stats[warp][0] = mean; stats[warp][1] = rstd; }
       }
       __syncthreads();
-      for (int cb = blockIdx.x; cb * (8 * CPW1) < H; cb += G) {
-        const int n_base = cb * (8 * CPW1) + warp * CPW1;
-        float acc[CPW1][kPT];
-#pragma unroll
-        for (int c = 0; c < CPW1; ++c)
-#pragma unroll
-          for (int j = 0; j < kPT; ++j) acc[c][j] = 0.f;
-        for (int k0 = 0; k0 < D; k0 += kKT) {
-          const int kt = min(kKT, D - k0), q4 = kt >> 2;
-          for (int idx = threadIdx.x; idx < kPT * q4; idx += 256) {
-            const int j = idx / q4, q = idx - j * q4, k = k0 + 4 * q;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < np) {
-              const float4 a = __ldcg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(p0 + j) * D + k));
-              const float4 t = *reinterpret_cast<const float4*>(tl + static_cast<int64_t>(p0 + j) * D + k);
-              const float4 g = __ldg(reinterpret_cast<const float4*>(L.ln2_g + k));
-              const float4 b = __ldg(reinterpret_cast<const float4*>(L.ln2_b + k));
-              const float mean = stats[j][0], rstd = stats[j][1];
-              v.x = ((a.x + t.x) - mean) * rstd * g.x + b.x;
-              v.y = ((a.y + t.y) - mean) * rstd * g.y + b.y;
-              v.z = ((a.z + t.z) - mean) * rstd * g.z + b.z;
-              v.w = ((a.w + t.w) - mean) * rstd * g.w + b.w;
-            }
-            *reinterpret_cast<float4*>(&xs[j][4 * q]) = v;
-          }
-          __syncthreads();
-          tile_dot<CPW1>(L.Wfc1, D, n_base, H, k0, kt, xs, lane, acc);
-          __syncthreads();
-        }
-        float a[CPW1 * kPT];
-#pragma unroll
-        for (int c = 0; c < CPW1; ++c)
-#pragma unroll
-          for (int j = 0; j < kPT; ++j) a[c * kPT + j] = acc[c][j];
-        butterfly<CPW1 * kPT>(a, lane);
-        const int c = lane / kPT, j = lane - c * kPT, n = n_base + c;
-        if (j < np && n < H) h[static_cast<int64_t>(p0 + j) * H + n] = gelu_erf(a[0] + L.bfc1[n]);
+      for (int idx = threadIdx.x; idx < np * (D >> 2); idx += 256) {    // normalise in place
+        const int j = idx / (D >> 2), k = 4 * (idx - j * (D >> 2));
+        float4 v = *reinterpret_cast<float4*>(xs + j * D + k);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(L.ln2_g + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(L.ln2_b + k));
+        const float mean = stats[j][0], rstd = stats[j][1];
+        v.x = (v.x - mean) * rstd * g.x + b.x;
+        v.y = (v.y - mean) * rstd * g.y + b.y;
+        v.z = (v.z - mean) * rstd * g.z + b.z;
+        v.w = (v.w - mean) * rstd * g.w + b.w;
+        *reinterpret_cast<float4*>(xs + j * D + k) = v;
       }
-      __syncthreads();  // stats / xs are reused by the next chunk of persons
+      __syncthreads();
+      for (int cb = blockIdx.x; cb * 32 < H; cb += G) {
+        const int ngroups = min(8, (H - cb * 32 + 3) / 4);
+        cta_linear(L.Wfc1, D, H, D, cb * 32, ngroups, xs, D, red, warp, lane, [&](int n, int j, float v) {
+          if (j < np) h[static_cast<int64_t>(p0 + j) * H + n] = gelu_erf(v + L.bfc1[n]);
+        });
+      }
     }
     for (int cb = blockIdx.x; cb * 8 < D; cb += G) prefetch_l2_rows(L.Wfc2, H, cb * 8, 8, D, H, warp, lane);
     grid_barrier(barrier, ++phase * G);
     // ---------------- phase 2: x = (x + term_l) + ls2 * (W_fc2 . h + b_fc2)
     for (int p0 = 0; p0 < P; p0 += kPT) {
       const int np = min(kPT, P - p0);
+      for (int idx = threadIdx.x; idx < kPT * (H >> 2); idx += 256) {
+        const int j = idx / (H >> 2), k = 4 * (idx - j * (H >> 2));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < np) v = __ldcg(reinterpret_cast<const float4*>(h + static_cast<int64_t>(p0 + j) * H + k));
+        *reinterpret_cast<float4*>(xs + j * H + k) = v;
+      }
+      __syncthreads();
       for (int cb = blockIdx.x; cb * 8 < D; cb += G) {
-        const int n_base = cb * 8 + warp * CPW2;
-        float acc[CPW2][kPT];
-#pragma unroll
-        for (int j = 0; j < kPT; ++j) acc[0][j] = 0.f;
-        for (int k0 = 0; k0 < H; k0 += kKT) {
-          const int kt = min(kKT, H - k0), q4 = kt >> 2;
-          for (int idx = threadIdx.x; idx < kPT * q4; idx += 256) {
-            const int j = idx / q4, q = idx - j * q4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < np) v = __ldcg(reinterpret_cast<const float4*>(h + static_cast<int64_t>(p0 + j) * H + k0 + 4 * q));
-            *reinterpret_cast<float4*>(&xs[j][4 * q]) = v;
+        const int ngroups = min(2, (D - cb * 8 + 3) / 4);
+        cta_linear(L.Wfc2, H, D, H, cb * 8, ngroups, xs, H, red, warp, lane, [&](int n, int j, float v) {
+          if (j < np) {
+            const int64_t o = static_cast<int64_t>(p0 + j) * D + n;
+            x[o] = (__ldcg(x + o) + tl[o]) + L.ls2[n] * (v + L.bfc2[n]);
           }
-          __syncthreads();
-          tile_dot<CPW2>(L.Wfc2, H, n_base, D, k0, kt, xs, lane, acc);
-          __syncthreads();
-        }
-        float a[CPW2 * kPT];
-#pragma unroll
-        for (int j = 0; j < kPT; ++j) a[j] = acc[0][j];
-        butterfly<CPW2 * kPT>(a, lane);
-        const int j = lane & (kPT - 1), n = n_base;
-        if (lane < kPT && j < np && n < D) {
-          const int64_t o = static_cast<int64_t>(p0 + j) * D + n;
-          x[o] = (__ldcg(x + o) + tl[o]) + L.ls2[n] * (a[0] + L.bfc2[n]);
-        }
+        });
       }
     }
     if (l + 1 < depth) {
       const RefineLayer Ln = layers[l + 1];
-      for (int cb = blockIdx.x; cb * (8 * CPW1) < H; cb += G) prefetch_l2_rows(Ln.Wfc1, D, cb * 8 * CPW1, 8 * CPW1, H, D, warp, lane);
+      for (int cb = blockIdx.x; cb * 32 < H; cb += G) prefetch_l2_rows(Ln.Wfc1, D, cb * 32, 32, H, D, warp, lane);
     }
     grid_barrier(barrier, ++phase * G);
   }
@@ -278,10 +311,16 @@ int refine_mlp_chain(const RefineLayer* layers, int depth, const int* count, int
   // cannot deadlock
   int grid = (4 * D + 31) / 32;
   if (grid > device_sm_count()) grid = device_sm_count();
+  const int smem = (kPT * 4 * D + 8 * 256) * static_cast<int>(sizeof(float));
+  MHMR_REQUIRE(smem <= 200 * 1024, "refine: embed dim too large for the staged hidden rows");
+  static PerDeviceOnce once;
+  if (once.first()) {
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(refine_mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
   void* args[] = {(void*)&layers, (void*)&depth, (void*)&count, (void*)&D, (void*)&max_persons,
                   (void*)&term,   (void*)&x,     (void*)&h,     (void*)&barrier};
   MHMR_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(refine_mlp_chain_kernel), dim3(grid), dim3(256),
-                                              args, 0, st));
+                                              args, smem, st));
   return MHMR_OK;
 }
 
