@@ -145,12 +145,16 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // 8 warps (each warp a contiguous K slice, every lane 4 consecutive k per 128-wide step), 4 columns at a time; the
 // per-warp partial sums go through shared memory (red[warp][group * 32 + lane]) and are added up by one thread per
 // (column, person).  Many independent weight loads in flight per lane, one pass over the staged rows per group.
+// 16 warps = 2 teams x 8 K-slices; team u takes the column groups u, u + 2, ...
+constexpr int kChainThreads = 512;
+
 template <typename Epi>
 __device__ __forceinline__ void cta_linear(const float* __restrict__ W, int64_t ldw, int Nout, int K, int n0, int ngroups,
                                            const float* xs, int ldxs, float* red, int warp, int lane, Epi epi) {
   const int slice = ((K / 8) + 3) & ~3;           // K slice of a warp (multiple of 4)
-  const int kbeg = warp * slice, kend = min(K, kbeg + slice);
-  for (int g = 0; g < ngroups; ++g) {
+  const int kw = warp & 7, team = warp >> 3;
+  const int kbeg = kw * slice, kend = min(K, kbeg + slice);
+  for (int g = team; g < ngroups; g += kChainThreads / 256) {
     const int n_base = n0 + 4 * g;
     float acc[4][kPT];
 #pragma unroll
@@ -177,7 +181,7 @@ __device__ __forceinline__ void cta_linear(const float* __restrict__ W, int64_t 
 #pragma unroll
       for (int j = 0; j < kPT; ++j) a[c * kPT + j] = acc[c][j];
     butterfly<4 * kPT>(a, lane);
-    red[warp * 256 + g * 32 + lane] = a[0];   // value index lane = (column c = lane / 8, person j = lane % 8)
+    red[kw * 256 + g * 32 + lane] = a[0];     // value index lane = (column c = lane / 8, person j = lane % 8)
   }
   __syncthreads();
   const int t = threadIdx.x;
@@ -193,7 +197,7 @@ __device__ __forceinline__ void cta_linear(const float* __restrict__ W, int64_t 
 }
 
 // ---- (B) the MLP chain of every block in one persistent cooperative kernel
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kChainThreads)
 refine_mlp_chain_kernel(const RefineLayer* __restrict__ layers, int depth, const int* __restrict__ count, int D,
                         int max_persons, const float* __restrict__ term, float* x, float* h, unsigned int* barrier) {
   extern __shared__ __align__(16) float dyn[];
@@ -213,7 +217,7 @@ refine_mlp_chain_kernel(const RefineLayer* __restrict__ layers, int depth, const
     // ---------------- phase 1: h = gelu(W_fc1 . LN2(x + term_l) + b_fc1)
     for (int p0 = 0; p0 < P; p0 += kPT) {
       const int np = min(kPT, P - p0);
-      for (int idx = threadIdx.x; idx < kPT * (D >> 2); idx += 256) {   // raw rows x + term
+      for (int idx = threadIdx.x; idx < kPT * (D >> 2); idx += kChainThreads) {   // raw rows x + term
         const int j = idx / (D >> 2), k = 4 * (idx - j * (D >> 2));
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < np) {
@@ -235,7 +239,7 @@ refine_mlp_chain_kernel(const RefineLayer* __restrict__ layers, int depth, const
         if (lane == 0) { stats[warp][0] = mean; stats[warp][1] = rstd; }
       }
       __syncthreads();
-      for (int idx = threadIdx.x; idx < np * (D >> 2); idx += 256) {    // normalise in place
+      for (int idx = threadIdx.x; idx < np * (D >> 2); idx += kChainThreads) {    // normalise in place
         const int j = idx / (D >> 2), k = 4 * (idx - j * (D >> 2));
         float4 v = *reinterpret_cast<float4*>(xs + j * D + k);
         const float4 g = __ldg(reinterpret_cast<const float4*>(L.ln2_g + k));
@@ -260,7 +264,7 @@ refine_mlp_chain_kernel(const RefineLayer* __restrict__ layers, int depth, const
     // ---------------- phase 2: x = (x + term_l) + ls2 * (W_fc2 . h + b_fc2)
     for (int p0 = 0; p0 < P; p0 += kPT) {
       const int np = min(kPT, P - p0);
-      for (int idx = threadIdx.x; idx < kPT * (H >> 2); idx += 256) {
+      for (int idx = threadIdx.x; idx < kPT * (H >> 2); idx += kChainThreads) {
         const int j = idx / (H >> 2), k = 4 * (idx - j * (H >> 2));
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < np) v = __ldcg(reinterpret_cast<const float4*>(h + static_cast<int64_t>(p0 + j) * H + k));
@@ -319,8 +323,8 @@ int refine_mlp_chain(const RefineLayer* layers, int depth, const int* count, int
   }
   void* args[] = {(void*)&layers, (void*)&depth, (void*)&count, (void*)&D, (void*)&max_persons,
                   (void*)&term,   (void*)&x,     (void*)&h,     (void*)&barrier};
-  MHMR_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(refine_mlp_chain_kernel), dim3(grid), dim3(256),
-                                              args, smem, st));
+  MHMR_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(refine_mlp_chain_kernel), dim3(grid),
+                                              dim3(kChainThreads), args, smem, st));
   return MHMR_OK;
 }
 
