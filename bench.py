@@ -424,7 +424,7 @@ def run_ours(args):
                 "persons": int(P_e2e)},
         "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -584,7 +584,29 @@ def run_reference(args):
                          "host": info, "sample": sample},
         "e2e": {"value": round(value, 5), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """stdout must carry exactly ONE JSON line: libraries (the NCCL version banner of a communicator, warnings of
+    child processes) write to fd 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON
+    line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -598,6 +620,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the short c2 (672x672) leg of the default run")
     args = ap.parse_args()
     set_workload(args.config)
+    _reserve_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -220,20 +220,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __half* __restr
       if (elect_one_sync()) {
         uint8_t* dq = sQ + qb * 2 * kTileBytes;
         mbar_arrive_expect_tx(&q_full[qb], a.two ? 2 * kTileBytes : kTileBytes);
-        tma_load_2d(dq, &tmQKV, &q_full[qb], a.head * kHeadDim, row0 + a.q0);
-        if (a.two) tma_load_2d(dq + kTileBytes, &tmQKV, &q_full[qb], a.head * kHeadDim, row0 + a.q0 + kBlockQ);
+        // Q is read once per item, K / V by every item of the (image, head): keep K / V in L2 (r02 capture of the
+        // persistent kernel without hints: 327 MB of DRAM reads per launch for 201 MB of qkv)
+        tma_load_2d_hint(dq, &tmQKV, &q_full[qb], a.head * kHeadDim, row0 + a.q0, kCacheEvictFirst);
+        if (a.two)
+          tma_load_2d_hint(dq + kTileBytes, &tmQKV, &q_full[qb], a.head * kHeadDim, row0 + a.q0 + kBlockQ, kCacheEvictFirst);
       }
       for (int j = 0; j < n_kv; ++j, ++kt) {
         const uint32_t sk = kt % kSK, sv = kt % kSV;
         mbar_wait(&k_empty[sk], ((kt / kSK) & 1u) ^ 1u);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&k_full[sk], kTileBytes);
-          tma_load_2d(sK + sk * kTileBytes, &tmQKV, &k_full[sk], D + a.head * kHeadDim, row0 + j * kBlockKV);
+          tma_load_2d_hint(sK + sk * kTileBytes, &tmQKV, &k_full[sk], D + a.head * kHeadDim, row0 + j * kBlockKV, kCacheEvictLast);
         }
         mbar_wait(&v_empty[sv], ((kt / kSV) & 1u) ^ 1u);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&v_full[sv], kTileBytes);
-          tma_load_2d(sV + sv * kTileBytes, &tmQKV, &v_full[sv], 2 * D + a.head * kHeadDim, row0 + j * kBlockKV);
+          tma_load_2d_hint(sV + sv * kTileBytes, &tmQKV, &v_full[sv], 2 * D + a.head * kHeadDim, row0 + j * kBlockKV, kCacheEvictLast);
         }
       }
     }

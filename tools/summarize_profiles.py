@@ -15,7 +15,7 @@ os.makedirs(out_dir, exist_ok=True)
 
 def short(name):
     name = re.sub(r"\(.*", "", name)
-    return re.sub(r"mhmr::\(anonymous namespace\)::|mhmr::<unnamed>::|void ", "", name)[:64]
+    return re.sub(r"mhmr::\(anonymous namespace\)::|mhmr::<unnamed>::|unnamed>::|<unnamed>::|void ", "", name)[:64]
 
 
 rows = [r for r in csv.reader(open(launches_csv)) if len(r) > 10]
