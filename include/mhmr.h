@@ -51,6 +51,21 @@ int mhmr_op_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int
                      void* out, int64_t ldo, int rows_in, int rows_out, int row_off, int block_n,
                      void* stream);
 
+/* One seam of a dinov2 Block with the LayerNorm folded into the GEMMs on both sides of it -- what the engine runs
+ * between attention and the MLP (and between one block's MLP and the next block's attention):
+ *     X += ls * (A @ Wp^T + bp)                       attn.proj / mlp.fc2 + LayerScale + residual (layers/block.py)
+ *     out16 = act(LayerNorm(X; ln_g, ln_b, eps 1e-6) @ W^T + b)      norm2 -> mlp.fc1 (+ GELU) / norm1 -> attn.qkv
+ * Between the two the residual stream is a two-term fp16 split X = hi + lo (22 significant bits, 4 bytes per element
+ * like fp32): the first GEMM's epilogue updates (hi, lo) in place and leaves per-row partial (sum, sum of squares); the
+ * second GEMM runs on the hi plane with the row-centred W * diag(ln_g) and applies 1/sigma in its epilogue.  A, Wp fp16
+ * (K contiguous); X fp32 [M, D] in place (split on entry, merged on exit); W fp32 [N, D] (folded and rounded inside);
+ * D multiple of 128 (<= 1024), N multiple of 32.
+ * Unit-test entry: allocates its temporaries and synchronises the stream. */
+int mhmr_op_resid_ln_linear_f16(const void* A, int64_t lda, const void* Wp, int64_t ldwp, const float* bp,
+                                const float* ls, float* X, int M, int D, int Ka, const float* ln_g,
+                                const float* ln_b, const float* W, const float* b, int N, int gelu, void* out16,
+                                int64_t ldo, void* stream);
+
 /* Multi-head self-attention of the ViT backbone, head dim 64: out[:, h*64:(h+1)*64] =
  * softmax(q_h k_h^T / 8) v_h per image.  qkv is [B*T, 3*D] fp16 (q | k | v column blocks, the layout the
  * qkv Linear produces), out is [B*T, D] fp16.  Replaces dinov2 Attention.forward's

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <map>
 #include <memory>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -34,6 +35,8 @@ struct VitLayer {
   __half *Wqkv, *Wproj, *Wfc1, *Wfc2;
   const float *Wproj32, *Wfc1_32, *Wfc2_32;  // fp32 masters (central-stream refinement)
   __half* O16;                               // this layer's attention output [max_batch*T, D]
+  // norm1 / norm2 folded into qkv / fc1 (gemm_tc.cuh): biases with the LayerNorm beta folded in
+  float *bqkv_f = nullptr, *bfc1_f = nullptr;
   GemmPlan qkv, proj, fc1, fc2;
 };
 struct HphLayer {
@@ -83,6 +86,10 @@ struct mhmr_engine {
 
   // workspaces
   __half *A16 = nullptr, *Xn16 = nullptr, *QKV16 = nullptr, *O16 = nullptr, *H16 = nullptr, *ctx16 = nullptr;
+  bool ln_fold = true;       // MHMR_LN_FOLD=0: separate LayerNorm kernels (A/B measurements)
+  float2* ln_stats = nullptr;  // [max_batch*T, ln_slots] partial row statistics of the residual stream
+  __half* Xlo = nullptr;       // lo plane of the two-term fp16 residual stream (hi plane = Xn16), gemm_tc.cuh
+  int ln_slots = 0;
   float *X = nullptr, *z32 = nullptr, *scores_raw = nullptr, *KV32 = nullptr, *Kinv = nullptr;
   int *det = nullptr, *count = nullptr, *img_off = nullptr;
   // central-stream refinement: token rows, input patches, residual streams and MLP hidden of the detected persons
@@ -182,6 +189,15 @@ int finalize_vit(mhmr_engine* e, cudaStream_t st) {
   const size_t o_layers = e->cfg.refine_central ? static_cast<size_t>(e->depth) : 1;
   TRY(e->alloc(&e->O16, o_layers * M * D));
   TRY(e->alloc(&e->H16, M * 4 * D));
+  {
+    const char* lf = std::getenv("MHMR_LN_FOLD");
+    e->ln_fold = !(lf != nullptr && lf[0] == '0');
+  }
+  e->ln_slots = gemm_stat_slots(D, pick_bn(D));
+  if (e->ln_fold) {
+    TRY(e->alloc(&e->ln_stats, M * e->ln_slots));
+    TRY(e->alloc(&e->Xlo, M * D));
+  }
 
   GemmEpi ep;
   ep.rowadd = e->rowadd; ep.out = e->X; ep.ldo = D; ep.rows_in = N; ep.rows_out = T; ep.row_off = 1;
@@ -202,18 +218,40 @@ int finalize_vit(mhmr_engine* e, cudaStream_t st) {
     L.Wproj32 = wproj; L.Wfc1_32 = wfc1; L.Wfc2_32 = wfc2;
     L.O16 = e->O16 + (e->cfg.refine_central ? static_cast<size_t>(l) * M * D : 0);
     L.bqkv = bqkv; L.bproj = bproj; L.ls1 = ls1; L.bfc1 = bfc1; L.bfc2 = bfc2; L.ls2 = ls2;
-    TRY(to_f16(e, wqkv, D, 3 * D, D, D, &L.Wqkv, st));
     TRY(to_f16(e, wproj, D, D, D, D, &L.Wproj, st));
-    TRY(to_f16(e, wfc1, D, 4 * D, D, D, &L.Wfc1, st));
     TRY(to_f16(e, wfc2, 4 * D, D, 4 * D, 4 * D, &L.Wfc2, st));
-    GemmEpi a; a.bias = bqkv; a.out = e->QKV16; a.ldo = 3 * D;
-    TRY(gemm_plan_init(&L.qkv, e->Xn16, D, L.Wqkv, D, static_cast<int>(M), 3 * D, D, EPI_BIAS_F16, a, pick_bn(3 * D)));
+    GemmEpi a; a.out = e->QKV16; a.ldo = 3 * D;
     GemmEpi p; p.bias = bproj; p.gamma = ls1; p.out = e->X; p.ldo = D;
-    TRY(gemm_plan_init(&L.proj, L.O16, D, L.Wproj, D, static_cast<int>(M), D, D, EPI_LS_RESID_F32, p, pick_bn(D)));
-    GemmEpi f1; f1.bias = bfc1; f1.out = e->H16; f1.ldo = 4 * D;
-    TRY(gemm_plan_init(&L.fc1, e->Xn16, D, L.Wfc1, D, static_cast<int>(M), 4 * D, D, EPI_BIAS_GELU_F16, f1, pick_bn(4 * D)));
+    GemmEpi f1; f1.out = e->H16; f1.ldo = 4 * D;
     GemmEpi f2; f2.bias = bfc2; f2.gamma = ls2; f2.out = e->X; f2.ldo = D;
-    TRY(gemm_plan_init(&L.fc2, e->H16, 4 * D, L.Wfc2, 4 * D, static_cast<int>(M), D, 4 * D, EPI_LS_RESID_F32, f2, pick_bn(D)));
+    int epi_qkv = EPI_BIAS_F16, epi_fc1 = EPI_BIAS_GELU_F16, epi_proj = EPI_LS_RESID_F32, epi_fc2 = EPI_LS_RESID_F32;
+    if (e->ln_fold) {
+      // qkv / fc1 read the hi plane of the residual stream that the previous proj / fc2 epilogue (layer 0:
+      // split_rowstats) left in Xn16, and normalise in their epilogue from the row statistics
+      TRY(e->alloc(&L.Wqkv, static_cast<size_t>(3) * D * D));
+      TRY(e->alloc(&L.bqkv_f, 3 * D));
+      TRY(fold_ln_linear(wqkv, bqkv, n1g, n1b, L.Wqkv, L.bqkv_f, 3 * D, D, st));
+      TRY(e->alloc(&L.Wfc1, static_cast<size_t>(4) * D * D));
+      TRY(e->alloc(&L.bfc1_f, 4 * D));
+      TRY(fold_ln_linear(wfc1, bfc1, n2g, n2b, L.Wfc1, L.bfc1_f, 4 * D, D, st));
+      a.bias = L.bqkv_f; a.stats = e->ln_stats; a.stat_slots = e->ln_slots;
+      f1.bias = L.bfc1_f; f1.stats = e->ln_stats; f1.stat_slots = e->ln_slots;
+      epi_qkv = EPI_LN_BIAS_F16;
+      epi_fc1 = EPI_LN_GELU_F16;
+      // the residual stream lives in (Xn16, Xlo) = (hi, lo); hi is the A operand of qkv / fc1
+      p.out = nullptr; p.x16 = e->Xn16; p.xlo = e->Xlo; p.ldx16 = D; p.stats = e->ln_stats; p.stat_slots = e->ln_slots;
+      f2.out = nullptr; f2.x16 = e->Xn16; f2.xlo = e->Xlo; f2.ldx16 = D; f2.stats = e->ln_stats; f2.stat_slots = e->ln_slots;
+      epi_proj = epi_fc2 = EPI_LS_RESID_SPLIT;
+    } else {
+      TRY(to_f16(e, wqkv, D, 3 * D, D, D, &L.Wqkv, st));
+      TRY(to_f16(e, wfc1, D, 4 * D, D, D, &L.Wfc1, st));
+      a.bias = bqkv;
+      f1.bias = bfc1;
+    }
+    TRY(gemm_plan_init(&L.qkv, e->Xn16, D, L.Wqkv, D, static_cast<int>(M), 3 * D, D, epi_qkv, a, pick_bn(3 * D)));
+    TRY(gemm_plan_init(&L.proj, L.O16, D, L.Wproj, D, static_cast<int>(M), D, D, epi_proj, p, pick_bn(D)));
+    TRY(gemm_plan_init(&L.fc1, e->Xn16, D, L.Wfc1, D, static_cast<int>(M), 4 * D, D, epi_fc1, f1, pick_bn(4 * D)));
+    TRY(gemm_plan_init(&L.fc2, e->H16, 4 * D, L.Wfc2, 4 * D, static_cast<int>(M), D, 4 * D, epi_fc2, f2, pick_bn(D)));
   }
   if (e->w(enc + "norm.weight", D) == nullptr || e->w(enc + "norm.bias", D) == nullptr) return MHMR_ERR_STATE;
   return MHMR_OK;
@@ -441,18 +479,29 @@ int vit_forward(mhmr_engine* e, const ImgSrc& x, int B, float* z_out, cudaStream
   TRY(run_plan(e, MHMR_CAT_GEMM_OTHER, e->patch_plan, B * N, st));
   for (int l = 0; l < e->depth; ++l) {
     VitLayer& L = e->vit[l];
-    LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln1_g, L.ln1_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
+    // norm1 / norm2: folded into qkv / fc1 (statistics + raw fp16 rows come from the previous epilogue), or kernels
+    if (!e->ln_fold) {
+      LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln1_g, L.ln1_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
+    } else if (l == 0) {
+      LAUNCH(MHMR_CAT_LAYERNORM, split_rowstats(e->X, e->Xn16, e->Xlo, D, e->ln_stats, e->ln_slots, M, D, st));
+    }
     TRY(run_plan(e, MHMR_CAT_GEMM_QKV, L.qkv, M, st));
     LAUNCH(MHMR_CAT_ATTENTION, attention_forward(e->QKV16, 3 * D, L.O16, D, B, T, D, st));
     TRY(run_plan(e, MHMR_CAT_GEMM_PROJ, L.proj, M, st));
-    LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln2_g, L.ln2_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
+    if (!e->ln_fold)
+      LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, L.ln2_g, L.ln2_b, e->Xn16, D, nullptr, 0, M, D, 1e-6f, 0, 0, st));
     TRY(run_plan(e, MHMR_CAT_GEMM_FC1, L.fc1, M, st));
     TRY(run_plan(e, MHMR_CAT_GEMM_FC2, L.fc2, M, st));
   }
   // final norm, cls dropped: fp32 features (head query side, optional user copy) + fp16 context columns
   const float* ng = e->w("backbone.encoder.norm.weight");
   const float* nb = e->w("backbone.encoder.norm.bias");
-  LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, ng, nb, e->ctx16, e->Cp, e->z32, D, M, D, 1e-6f, T, 1, st));
+  if (e->ln_fold) {
+    LAUNCH(MHMR_CAT_LAYERNORM,
+           layernorm_split(e->Xn16, e->Xlo, ng, nb, e->ctx16, e->Cp, e->z32, D, M, D, 1e-6f, T, 1, st));
+  } else {
+    LAUNCH(MHMR_CAT_LAYERNORM, layernorm(e->X, ng, nb, e->ctx16, e->Cp, e->z32, D, M, D, 1e-6f, T, 1, st));
+  }
   if (z_out != nullptr)
     MHMR_CUDA_CHECK(cudaMemcpyAsync(z_out, e->z32, static_cast<size_t>(B) * N * D * 4, cudaMemcpyDeviceToDevice, st));
   return MHMR_OK;

@@ -137,13 +137,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int par = (warp - 4) >> 2;     // two warps per sub-partition split the column chunks
     float* scratch = scratch_base + (warp - 4) * (kScratchBytes / 4);
     uint32_t acc_iter = 0;
+    EpiStatsPrefetch pf;
+    if (static_cast<int>(blockIdx.x) < num_tiles)
+      epilogue_load_row_stats<EPI>(pf, ep, M, (static_cast<int>(blockIdx.x) / num_n) * BM + ew * 32, lane);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_iter) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const uint32_t as = acc_iter & 1u;
       const uint32_t aphase = (acc_iter >> 1) & 1u;
+      const int m_base = m_blk * BM + ew * 32;
+      EpiRowState rowst;
+      epilogue_tile_begin<EPI>(rowst, pf, ep, K);
+      if (tile + static_cast<int>(gridDim.x) < num_tiles)  // next tile's row statistics: under this tile's epilogue
+        epilogue_load_row_stats<EPI>(pf, ep, M, ((tile + static_cast<int>(gridDim.x)) / num_n) * BM + ew * 32, lane);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int m_base = m_blk * BM + ew * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       constexpr int kChunksPerWarp = BN / 32 / (kEpiWarps / 4);
 #pragma unroll 1
@@ -158,8 +165,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
         const int n0 = n_blk * BN + c * 32;
-        if (n0 < N) epilogue_chunk<EPI>(r, scratch, ep, M, N, m_base, n0, lane);
+        if (n0 < N) epilogue_chunk<EPI>(r, scratch, ep, M, N, m_base, n0, lane, rowst);
       }
+      epilogue_tile_end<EPI>(rowst, ep, M, m_base, n_blk * (kEpiWarps / 4) + par, lane);
     }
   }
 
@@ -203,6 +211,9 @@ int launch_bn(const GemmPlan* p, cudaStream_t stream) {
     case EPI_LS_RESID_F32: return launch_one<BN, EPI_LS_RESID_F32>(p, stream);
     case EPI_ROWADD_F32: return launch_one<BN, EPI_ROWADD_F32>(p, stream);
     case EPI_BIAS_F32: return launch_one<BN, EPI_BIAS_F32>(p, stream);
+    case EPI_LS_RESID_SPLIT: return launch_one<BN, EPI_LS_RESID_SPLIT>(p, stream);
+    case EPI_LN_BIAS_F16: return launch_one<BN, EPI_LN_BIAS_F16>(p, stream);
+    case EPI_LN_GELU_F16: return launch_one<BN, EPI_LN_GELU_F16>(p, stream);
     default: break;
   }
   set_last_error("gemm: unknown epilogue kind");
@@ -220,10 +231,19 @@ int gemm_plan_init(GemmPlan* plan, const __half* A, int64_t lda, const __half* W
                "gemm: operands must be 16-byte aligned");
   MHMR_REQUIRE(bn == 128 || bn == 256 || bn == 512, "gemm: block_n must be 128, 256 or 512 (CTA pair)");
   MHMR_REQUIRE(epi_kind >= 0 && epi_kind < EPI_NUM_KINDS, "gemm: bad epilogue kind");
-  MHMR_REQUIRE(ep.out != nullptr && ep.ldo % 8 == 0, "gemm: output missing or pitch not multiple of 8");
+  if (epi_kind != EPI_LS_RESID_SPLIT)
+    MHMR_REQUIRE(ep.out != nullptr && ep.ldo % 8 == 0, "gemm: output missing or pitch not multiple of 8");
   if (epi_kind != EPI_BIAS_F32 && epi_kind != EPI_ROWADD_F32)
     MHMR_REQUIRE(ep.bias != nullptr, "gemm: bias required for this epilogue");
-  if (epi_kind == EPI_LS_RESID_F32) MHMR_REQUIRE(ep.gamma != nullptr, "gemm: gamma required");
+  if (epi_kind == EPI_LS_RESID_F32 || epi_kind == EPI_LS_RESID_SPLIT)
+    MHMR_REQUIRE(ep.gamma != nullptr, "gemm: gamma required");
+  if (epi_kind == EPI_LS_RESID_SPLIT)
+    MHMR_REQUIRE(ep.x16 != nullptr && ep.xlo != nullptr && ep.ldx16 % 8 == 0 && ep.stats != nullptr &&
+                     ep.stat_slots == gemm_stat_slots(N, bn) && N % (bn == 128 ? 128 : 256) == 0,
+                 "gemm: split-stream epilogue needs both planes, stats, whole column tiles and matching slot count");
+  if (epi_kind == EPI_LN_BIAS_F16 || epi_kind == EPI_LN_GELU_F16)
+    MHMR_REQUIRE(ep.stats != nullptr && ep.stat_slots > 0 && ep.stat_slots % 2 == 0 && ep.stat_slots <= 8,
+                 "gemm: folded-LN consumer needs row statistics (even slot count, at most 8)");
   if (epi_kind == EPI_ROWADD_F32)
     MHMR_REQUIRE(ep.rowadd != nullptr && ep.rows_in > 0, "gemm: rowadd/rows_in required");
   plan->M = M; plan->N = N; plan->K = K; plan->bn = bn; plan->epi = epi_kind; plan->ep = ep;
@@ -246,6 +266,11 @@ int gemm_plan_grid(const GemmPlan* plan, int M) {
   }
   const int tiles = ((M + BM - 1) / BM) * ((plan->N + plan->bn - 1) / plan->bn);
   return tiles < sms ? tiles : sms;
+}
+
+int gemm_stat_slots(int N, int bn) {
+  const int tile_n = (bn == 128) ? 128 : 256;  // bn 512 = CTA pair with 256-column tiles
+  return ((N + tile_n - 1) / tile_n) * (kEpiWarps / 4);
 }
 
 int gemm_plan_run(const GemmPlan* plan, cudaStream_t stream) {

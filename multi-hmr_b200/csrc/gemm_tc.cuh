@@ -10,6 +10,19 @@
 //   EPI_LS_RESID_F32   out32 += gamma * (acc + bias)  in place  (attn.proj / mlp.fc2 + LayerScale + residual)
 //   EPI_ROWADD_F32     out32[remap(m)] = acc + rowadd[m % rows_in]  (patch-embed + bias + pos-embed scatter)
 //   EPI_BIAS_F32       out32 = acc + bias (bias may be null)    (HPH to_kv, cross_attn_transformer.py:187)
+//
+// LayerNorm folded into the two Linears that follow it (dinov2 Block: norm1 -> attn.qkv, norm2 -> mlp.fc1).
+// With W'[n,k] = W[n,k] ln_gamma[k] - mean_k(W[n,:] ln_gamma) (rows centred, rounded to fp16) and
+// b'[n] = b[n] + sum_k ln_beta[k] W[n,k]:
+//     Linear(LN(x))[n] = rstd * sum_k x[k] W'[n,k] + b'[n]        (sum_k (x[k] - mean) W'[n,k] = sum_k x[k] W'[n,k])
+// so the GEMM runs on the RAW residual stream and only 1/sigma enters, in the epilogue.  The raw fp16 operand costs
+// nothing extra because the residual stream itself is kept as a two-term fp16 split x = hi + lo (22 significant
+// bits; hi = fp16(x) IS the tensor-core operand, lo = fp16(x - hi)), the same 4 bytes per element as fp32:
+//   EPI_LS_RESID_SPLIT   x = (hi + lo) + gamma * (acc + bias), written back as (hi, lo) in place, + per-row partial
+//                        (sum, sum of squares) of the new x over the columns one epilogue warp owns:
+//                        stats[m][slot], slot = 2 n_blk + par                  (attn.proj / mlp.fc2 + LayerScale)
+//   EPI_LN_BIAS_F16      out16 = rstd acc + b'                       statistics reduced from stats[m][0..slots)
+//   EPI_LN_GELU_F16      out16 = gelu_erf(rstd acc + b')
 #pragma once
 #include "common.cuh"
 
@@ -22,7 +35,11 @@ enum GemmEpiKind : int {
   EPI_LS_RESID_F32 = 3,
   EPI_ROWADD_F32 = 4,
   EPI_BIAS_F32 = 5,
-  EPI_NUM_KINDS = 6,
+  EPI_NUM_PUBLIC_KINDS = 6,   // what mhmr_op_gemm_f16 accepts
+  EPI_LS_RESID_SPLIT = 6,
+  EPI_LN_BIAS_F16 = 7,
+  EPI_LN_GELU_F16 = 8,
+  EPI_NUM_KINDS = 9,
 };
 
 struct GemmEpi {
@@ -33,6 +50,13 @@ struct GemmEpi {
   int64_t ldo = 0;
   // Row remap: out_row = (m / rows_in) * rows_out + row_off + (m % rows_in); rows_in == 0 => identity.
   int rows_in = 0, rows_out = 0, row_off = 0;
+  // folded LayerNorm (see above)
+  __half* x16 = nullptr;          // [M, ldx16] hi plane of the residual stream  (EPI_LS_RESID_SPLIT, in place)
+  __half* xlo = nullptr;          // [M, ldx16] lo plane
+  int64_t ldx16 = 0;
+  float2* stats = nullptr;        // [M, stat_slots] partial (sum, sumsq)   (written by RESID_SPLIT, read by LN_*)
+  int stat_slots = 0;
+  float ln_eps = 1e-6f;
 };
 
 struct GemmPlan {
@@ -51,5 +75,7 @@ int gemm_plan_run(const GemmPlan* plan, cudaStream_t stream);
 int gemm_plan_run_2cta(const GemmPlan* plan, cudaStream_t stream);  // gemm_tc2.cu
 // launch geometry for `M` rows with this plan's tile shape
 int gemm_plan_grid(const GemmPlan* plan, int M);
+// partial-statistics slots per row that an EPI_LS_RESID_SPLIT GEMM with N columns and tile selector `bn` writes
+int gemm_stat_slots(int N, int bn);
 
 }  // namespace mhmr

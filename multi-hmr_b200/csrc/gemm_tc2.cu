@@ -151,8 +151,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int m0 = m_blk * BM2 + static_cast<int>(rank) * 128;
       const int n0 = n_blk * BN2 + static_cast<int>(rank) * (BN2 / 2);
-      if constexpr (EPI == EPI_LS_RESID_F32) {
-        // The epilogue of proj / fc2 reads 128 KB of the fp32 residual stream per tile straight from HBM (written a
+      if constexpr (EPI == EPI_LS_RESID_F32 || EPI == EPI_LS_RESID_SPLIT) {
+        // The epilogue of proj / fc2 reads 128 KB of the residual stream per tile straight from HBM (written a
         // whole layer ago) and is latency-bound on it (r01: proj at 44 % DRAM).  The producer warp runs at most the
         // smem ring ahead of the tensor pipe: when it starts a tile it pulls that tile's residual rows into L2, a
         // whole main loop before the epilogue asks for them (prefetch.global.L2 is a hint: no hazard with the
@@ -161,9 +161,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int ncols = min(BN2, N - nc0);
         for (int r = lane; r < 128; r += 32) {
           if (m0 + r >= M) break;
-          const char* row = reinterpret_cast<const char*>(reinterpret_cast<const float*>(ep.out) +
-                                                          static_cast<int64_t>(m0 + r) * ep.ldo + nc0);
-          for (int b = 0; b < ncols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+          if constexpr (EPI == EPI_LS_RESID_F32) {
+            const char* row = reinterpret_cast<const char*>(reinterpret_cast<const float*>(ep.out) +
+                                                            static_cast<int64_t>(m0 + r) * ep.ldo + nc0);
+            for (int b = 0; b < ncols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+          } else {
+            const int64_t off = static_cast<int64_t>(m0 + r) * ep.ldx16 + nc0;
+            const char* rh = reinterpret_cast<const char*>(ep.x16 + off);
+            const char* rl = reinterpret_cast<const char*>(ep.xlo + off);
+            for (int b = 0; b < ncols * 2; b += 128) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rh + b));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rl + b));
+            }
+          }
         }
         __syncwarp();
       }
@@ -217,13 +227,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int par = (warp - 4) >> 2;
     float* scratch = scratch_base + (warp - 4) * (kScratchBytes / 4);
     uint32_t acc_iter = 0;
+    const int m_off = static_cast<int>(rank) * 128 + ew * 32;
+    EpiStatsPrefetch pf;
+    if (pair < num_tiles) epilogue_load_row_stats<EPI>(pf, ep, M, (pair / num_n) * BM2 + m_off, lane);
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++acc_iter) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const uint32_t as = acc_iter & 1u;
       const uint32_t aphase = (acc_iter >> 1) & 1u;
+      const int m_base = m_blk * BM2 + m_off;
+      EpiRowState rowst;
+      epilogue_tile_begin<EPI>(rowst, pf, ep, K);
+      if (tile + num_pairs < num_tiles)  // the next tile's row statistics travel under this tile's epilogue
+        epilogue_load_row_stats<EPI>(pf, ep, M, ((tile + num_pairs) / num_n) * BM2 + m_off, lane);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int m_base = m_blk * BM2 + static_cast<int>(rank) * 128 + ew * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN2;
       constexpr int kChunksPerWarp = BN2 / 32 / (kEpiWarps2 / 4);
 #pragma unroll 1
@@ -241,8 +258,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         const int n0 = n_blk * BN2 + c * 32;
-        if (n0 < N) epilogue_chunk<EPI>(r, scratch, ep, M, N, m_base, n0, lane);
+        if (n0 < N) epilogue_chunk<EPI>(r, scratch, ep, M, N, m_base, n0, lane, rowst);
       }
+      epilogue_tile_end<EPI>(rowst, ep, M, m_base, n_blk * (kEpiWarps2 / 4) + par, lane);
     }
   }
 
@@ -289,6 +307,9 @@ int gemm_plan_run_2cta(const GemmPlan* p, cudaStream_t stream) {
     case EPI_LS_RESID_F32: return launch_2cta<EPI_LS_RESID_F32>(p, stream);
     case EPI_ROWADD_F32: return launch_2cta<EPI_ROWADD_F32>(p, stream);
     case EPI_BIAS_F32: return launch_2cta<EPI_BIAS_F32>(p, stream);
+    case EPI_LS_RESID_SPLIT: return launch_2cta<EPI_LS_RESID_SPLIT>(p, stream);
+    case EPI_LN_BIAS_F16: return launch_2cta<EPI_LN_BIAS_F16>(p, stream);
+    case EPI_LN_GELU_F16: return launch_2cta<EPI_LN_GELU_F16>(p, stream);
     default: break;
   }
   set_last_error("gemm: unknown epilogue kind");

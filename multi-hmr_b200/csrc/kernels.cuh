@@ -18,6 +18,16 @@ int layernorm(const float* X, const float* gamma, const float* beta, __half* out
               cudaStream_t stream);
 int f32_to_f16_2d(const float* src, int64_t lds, __half* dst, int64_t ldd, int rows, int cols,
                   cudaStream_t stream);
+// folded LayerNorm (gemm_tc.cuh): entry kernel of the chain and the load-time weight folding
+int split_rowstats(const float* X, __half* xhi, __half* xlo, int64_t ld16, float2* stats, int slots, int M, int D,
+                   cudaStream_t stream);
+int merge_split(const __half* xhi, const __half* xlo, float* X, int64_t n, cudaStream_t stream);
+// LayerNorm of a two-term fp16 stream (X = hi plane, Xlo = lo plane; Xlo == nullptr: X is fp32)
+int layernorm_split(const void* X, const __half* Xlo, const float* gamma, const float* beta, __half* out16,
+                    int64_t ld16, float* out32, int64_t ld32, int M, int D, float eps, int rows_in, int skip,
+                    cudaStream_t stream);
+int fold_ln_linear(const float* W, const float* bias, const float* ln_g, const float* ln_b, __half* W16,
+                   float* bias2, int N, int K, cudaStream_t stream);
 int repack_f32(const float* src, int64_t lds, int scol, float* dst, int64_t ldd, int dcol, int rows,
                int cols, bool zero_fill, cudaStream_t stream);
 int add_vec(const float* a, const float* b, float* out, int64_t n, int64_t b_period, cudaStream_t stream);

@@ -90,8 +90,10 @@ __global__ void cls_row_kernel(float* __restrict__ X, const float* __restrict__ 
 // One warp per row.  Two-pass statistics in registers (mean, then centred sum of squares) in fp32.
 // Row remap (for the final norm, which drops the cls token): input row r = g*rows_in + t is skipped when
 // t < skip, else written to output row g*(rows_in - skip) + (t - skip).
+// With `Xlo` set, `X` is the hi plane of a two-term fp16 stream (gemm_tc.cuh) and the row is hi + lo.
 template <int VEC>  // D == 128 * VEC  (VEC float4 per lane)
-__global__ void layernorm_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
+__global__ void layernorm_kernel(const float* __restrict__ X, const __half* __restrict__ Xlo,
+                                 const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ out16, int64_t ld16,
                                  float* __restrict__ out32, int64_t ld32, int M, int D, float eps,
                                  int rows_in, int skip) {
@@ -105,14 +107,27 @@ __global__ void layernorm_kernel(const float* __restrict__ X, const float* __res
     if (t < skip) return;
     orow = static_cast<int64_t>(g) * (rows_in - skip) + (t - skip);
   }
-  const float4* xr = reinterpret_cast<const float4*>(X + static_cast<int64_t>(row) * D);
   float4 v[VEC];
   float s = 0.f;
+  if (Xlo == nullptr) {
+    const float4* xr = reinterpret_cast<const float4*>(X + static_cast<int64_t>(row) * D);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    v[i] = xr[lane + 32 * i];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int i = 0; i < VEC; ++i) v[i] = xr[lane + 32 * i];
+  } else {
+    const uint2* hr = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(X) + static_cast<int64_t>(row) * D);
+    const uint2* lr = reinterpret_cast<const uint2*>(Xlo + static_cast<int64_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const uint2 h = hr[lane + 32 * i], l = lr[lane + 32 * i];
+      const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+      const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+      const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x));
+      const float2 l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+      v[i] = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+    }
   }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) / D;
   float q = 0.f;
 #pragma unroll
@@ -141,6 +156,70 @@ __global__ void layernorm_kernel(const float* __restrict__ X, const float* __res
       reinterpret_cast<uint2*>(out16 + orow * ld16)[lane + 32 * i] = pk;
     }
   }
+}
+
+// Entry of the folded-LayerNorm chain (gemm_tc.cuh): the fp32 tokens (patch embedding + position) become the two-term
+// fp16 residual stream x = hi + lo, with (sum, sum of squares) of every row in slot 0 of its statistics and the other
+// slots cleared.  Layer 0 only: later layers get all three from the epilogue of attn.proj / mlp.fc2.  One warp per row.
+template <int VEC>
+__global__ void split_rowstats_kernel(const float* __restrict__ X, __half* __restrict__ xhi, __half* __restrict__ xlo,
+                                      int64_t ld16, float2* __restrict__ stats, int slots, int M, int D) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(X + static_cast<int64_t>(row) * D);
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 v = xr[lane + 32 * i];
+    s += (v.x + v.y) + (v.z + v.w);
+    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    uint2 ph, pl;
+    ph.x = *reinterpret_cast<const uint32_t*>(&h0);
+    ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+    pl.x = *reinterpret_cast<const uint32_t*>(&l0);
+    pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+    reinterpret_cast<uint2*>(xhi + static_cast<int64_t>(row) * ld16)[lane + 32 * i] = ph;
+    reinterpret_cast<uint2*>(xlo + static_cast<int64_t>(row) * ld16)[lane + 32 * i] = pl;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane < slots)
+    stats[static_cast<int64_t>(row) * slots + lane] = (lane == 0) ? make_float2(s, q) : make_float2(0.f, 0.f);
+}
+
+// fp32 view of a two-term fp16 stream (unit-test entry mhmr_op_resid_ln_linear_f16).
+__global__ void merge_split_kernel(const __half* __restrict__ xhi, const __half* __restrict__ xlo,
+                                   float* __restrict__ X, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    X[i] = __half2float(xhi[i]) + __half2float(xlo[i]);
+}
+
+// Load-time folding of a LayerNorm into the Linear that follows it (gemm_tc.cuh): one warp per output feature.
+//   W16[n,k] = fp16(W[n,k] ln_gamma[k] - mean_k(W[n,:] ln_gamma));   bias2[n] = bias[n] + sum_k ln_beta[k] W[n,k]
+// Rows of the folded weight are centred: sum_k x[k] W16[n,k] then already equals sum_k (x[k] - mean(x)) W'[n,k].
+__global__ void fold_ln_linear_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                      const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                      __half* __restrict__ W16, float* __restrict__ bias2, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  const float* wr = W + static_cast<int64_t>(n) * K;
+  float c = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = wr[k];
+    c += w * ln_g[k];
+    bb += ln_b[k] * w;
+  }
+  const float mean = warp_sum(c) / static_cast<float>(K);
+  bb = warp_sum(bb);
+  for (int k = lane; k < K; k += 32)
+    W16[static_cast<int64_t>(n) * K + k] = __float2half_rn(wr[k] * ln_g[k] - mean);
+  if (lane == 0) bias2[n] = bias[n] + bb;
 }
 
 __global__ void f32_to_f16_2d_kernel(const float* __restrict__ src, int64_t lds, __half* __restrict__ dst,
@@ -191,14 +270,20 @@ int cls_rows(float* X, const float* cls_pos, int B, int T, int D, cudaStream_t s
 int layernorm(const float* X, const float* gamma, const float* beta, __half* out16, int64_t ld16,
               float* out32, int64_t ld32, int M, int D, float eps, int rows_in, int skip,
               cudaStream_t stream) {
+  return layernorm_split(X, nullptr, gamma, beta, out16, ld16, out32, ld32, M, D, eps, rows_in, skip, stream);
+}
+
+int layernorm_split(const void* X, const __half* Xlo, const float* gamma, const float* beta, __half* out16,
+                    int64_t ld16, float* out32, int64_t ld32, int M, int D, float eps, int rows_in, int skip,
+                    cudaStream_t stream) {
   MHMR_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D must be a multiple of 128, <= 1024");
   MHMR_REQUIRE(out16 != nullptr || out32 != nullptr, "layernorm: no output");
   const int wpb = 8;
   dim3 grid((M + wpb - 1) / wpb), block(wpb * 32);
 #define MHMR_LN_CASE(V)                                                                              \
   case V:                                                                                            \
-    layernorm_kernel<V><<<grid, block, 0, stream>>>(X, gamma, beta, out16, ld16, out32, ld32, M, D, \
-                                                    eps, rows_in, skip);                            \
+    layernorm_kernel<V><<<grid, block, 0, stream>>>(static_cast<const float*>(X), Xlo, gamma, beta, out16, ld16, \
+                                                    out32, ld32, M, D, eps, rows_in, skip);          \
     break;
   switch (D / 128) {
     MHMR_LN_CASE(1) MHMR_LN_CASE(2) MHMR_LN_CASE(3) MHMR_LN_CASE(4) MHMR_LN_CASE(5) MHMR_LN_CASE(6)
@@ -206,6 +291,36 @@ int layernorm(const float* X, const float* gamma, const float* beta, __half* out
     default: break;
   }
 #undef MHMR_LN_CASE
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+int split_rowstats(const float* X, __half* xhi, __half* xlo, int64_t ld16, float2* stats, int slots, int M, int D,
+                   cudaStream_t stream) {
+  MHMR_REQUIRE(D % 128 == 0 && D <= 1024 && slots >= 1 && slots <= 32, "split_rowstats: bad geometry");
+  const int wpb = 8;
+  dim3 grid((M + wpb - 1) / wpb), block(wpb * 32);
+#define MHMR_CS_CASE(V) \
+  case V: split_rowstats_kernel<V><<<grid, block, 0, stream>>>(X, xhi, xlo, ld16, stats, slots, M, D); break;
+  switch (D / 128) {
+    MHMR_CS_CASE(1) MHMR_CS_CASE(2) MHMR_CS_CASE(3) MHMR_CS_CASE(4) MHMR_CS_CASE(5) MHMR_CS_CASE(6)
+    MHMR_CS_CASE(7) MHMR_CS_CASE(8)
+    default: break;
+  }
+#undef MHMR_CS_CASE
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+int merge_split(const __half* xhi, const __half* xlo, float* X, int64_t n, cudaStream_t stream) {
+  merge_split_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 16)), 256, 0, stream>>>(xhi, xlo, X, n);
+  MHMR_CUDA_CHECK(cudaGetLastError());
+  return MHMR_OK;
+}
+
+int fold_ln_linear(const float* W, const float* bias, const float* ln_g, const float* ln_b, __half* W16,
+                   float* bias2, int N, int K, cudaStream_t stream) {
+  fold_ln_linear_kernel<<<(N + 7) / 8, 256, 0, stream>>>(W, bias, ln_g, ln_b, W16, bias2, N, K);
   MHMR_CUDA_CHECK(cudaGetLastError());
   return MHMR_OK;
 }

@@ -36,6 +36,25 @@ def gemm_f16(a, w, epilogue, out, bias=None, gamma=None, rowadd=None, rows_in=0,
     return out
 
 
+def resid_ln_linear_f16(a, wp, bp, ls, x, ln_g, ln_b, w, b, gelu=False):
+    """One dinov2 Block seam with the LayerNorm folded into both GEMMs (see include/mhmr.h):
+    x += ls * (a @ wp^T + bp) in place (fp32 [M, D]); returns fp16 act(LayerNorm(x) @ w^T + b) of shape [M, N]."""
+    _cuda(a, wp, bp, ls, x, ln_g, ln_b, w, b)
+    assert a.dtype == torch.float16 and wp.dtype == torch.float16 and x.dtype == torch.float32
+    assert w.dtype == torch.float32 and a.stride(1) == 1 and wp.stride(1) == 1 and x.is_contiguous() and w.is_contiguous()
+    M, Ka = a.shape
+    D = wp.shape[0]
+    N = w.shape[0]
+    assert x.shape == (M, D) and w.shape == (N, D)
+    out = torch.empty(M, N, device=a.device, dtype=torch.float16)
+    rc = _lib.load().mhmr_op_resid_ln_linear_f16(
+        ptr(a), c_int64(a.stride(0)), ptr(wp), c_int64(wp.stride(0)), ptr(bp), ptr(ls), ptr(x), c_int(M), c_int(D),
+        c_int(Ka), ptr(ln_g), ptr(ln_b), ptr(w), ptr(b), c_int(N), c_int(1 if gelu else 0), ptr(out),
+        c_int64(out.stride(0)), stream_ptr())
+    check(rc, "mhmr_op_resid_ln_linear_f16")
+    return out
+
+
 def normalize_u8(img_u8, lut):
     """uint8 [B,H,W,3] -> fp32 [B,3,H,W]: out[b,c,y,x] = lut[c, img[b,y,x,c]] (device-side `normalize_rgb`)."""
     _cuda(img_u8, lut)

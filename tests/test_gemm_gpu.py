@@ -121,3 +121,61 @@ def test_gemm_rejects_bad_args(cuda_device):
     out = torch.zeros(16, 48, device=cuda_device, dtype=torch.float16)
     with pytest.raises(AssertionError):
         ops.gemm_f16(a, w, ops.EPI_BIAS_F16, out, bias=torch.zeros(48, device=cuda_device))
+
+
+@pytest.mark.parametrize("D,N,Ka,M,gelu", [
+    (1024, 4096, 1024, 4097 * 2 + 3, True),    # ViT-L norm2 -> fc1 (CTA pairs on both sides), ragged M
+    (1024, 3072, 4096, 2305, False),           # ViT-L fc2 -> next block's norm1 -> qkv
+    (768, 2304, 768, 1000, False),             # ViT-B
+    (384, 1536, 384, 1370, True),              # ViT-S: single-CTA producer (N = 384), CTA-pair consumer
+    (384, 1152, 1536, 257, False),             # ViT-S qkv: single-CTA kernels on both sides
+])
+def test_folded_layernorm_seam(cuda_device, D, N, Ka, M, gelu):
+    """proj / fc2 epilogue emits the raw fp16 rows + row statistics, the next GEMM normalises in its epilogue:
+    compared with the unfused fp32 chain (residual update -> LayerNorm -> Linear -> GELU) of the reference block
+    (dinov2 layers/block.py), on a stream with a non-zero mean and a few massive channels."""
+    from multihmr_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(D + N + M)
+    a = torch.randn(M, Ka, generator=g).to(cuda_device).half()
+    wp = (torch.randn(D, Ka, generator=g) * (1.0 / Ka ** 0.5)).to(cuda_device).half()
+    bp = (torch.randn(D, generator=g) * 0.1).to(cuda_device)
+    ls = (torch.rand(D, generator=g) * 0.5 + 0.1).to(cuda_device)
+    x0 = torch.randn(M, D, generator=g) * 1.5 + 0.7               # row mean about half a sigma
+    x0[:, 5] += 60.0                                              # massive channels (DINOv2-like outliers)
+    x0[: M // 3, 77] -= 35.0
+    x0 = x0.to(cuda_device)
+    ln_g = (torch.rand(D, generator=g) + 0.5).to(cuda_device)
+    ln_b = (torch.randn(D, generator=g) * 0.2).to(cuda_device)
+    w = (torch.randn(N, D, generator=g) * (1.0 / D ** 0.5)).to(cuda_device)
+    b = (torch.randn(N, generator=g) * 0.1).to(cuda_device)
+
+    x = x0.clone()
+    out = ops.resid_ln_linear_f16(a, wp, bp, ls, x, ln_g, ln_b, w, b, gelu=gelu)
+    x_ref = x0 + ls * (_ref_linear(a, wp) + bp)
+    assert (x - x_ref).abs().max().item() <= 2e-4
+    # fp64 reference of the normalised Linear on the reference stream
+    xr = x_ref.double()
+    y = torch.nn.functional.layer_norm(xr, (D,), ln_g.double(), ln_b.double(), eps=1e-6) @ w.double().t() + b.double()
+    if gelu:
+        y = torch.nn.functional.gelu(y)
+    err = (out.double() - y).abs()
+    # what the unfused fp16 path gives on the same data: fp16(LN(x)) @ fp16(W) -- the folded path must be no worse
+    # than 1.5x of it (same rounding points: one fp16 rounding per activation and per weight)
+    ln16 = torch.nn.functional.layer_norm(x_ref, (D,), ln_g, ln_b, eps=1e-6).half()
+    y16 = ln16.float() @ w.half().float().t() + b
+    if gelu:
+        y16 = torch.nn.functional.gelu(y16)
+    err16 = (y16.half().double() - y).abs()
+    assert err.max().item() <= 1.5 * err16.max().item() + 1e-3, (err.max().item(), err16.max().item())
+    assert err.pow(2).mean().sqrt().item() <= 1.25 * err16.pow(2).mean().sqrt().item() + 1e-5
+
+
+def test_public_gemm_rejects_internal_epilogues(cuda_device):
+    from multihmr_b200 import ops
+
+    a = torch.zeros(128, 64, device=cuda_device, dtype=torch.float16)
+    w = torch.zeros(128, 64, device=cuda_device, dtype=torch.float16)
+    out = torch.zeros(128, 128, device=cuda_device, dtype=torch.float16)
+    with pytest.raises(AssertionError):
+        ops.gemm_f16(a, w, 7, out, bias=torch.zeros(128, device=cuda_device), block_n=128)
