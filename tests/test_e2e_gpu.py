@@ -236,3 +236,30 @@ def test_head_stage_vs_oracle_on_engine_features(cuda_device):
         e = (got[k] - want[k]).abs().max().item()
         print(f"  head stage {k:12s} err {e:.3e} (tol {tol[k]:.0e})")
         assert e <= tol[k], (k, e)
+
+
+def test_separate_layernorm_path_stays_green(cuda_device):
+    """`MHMR_LN_FOLD=0` (fp32 residual stream + LayerNorm kernels: the A/B side of DESIGN.md §5 "LayerNorm folded into
+    the GEMMs") must keep matching the reference goldens; the switch is read once per engine, so a child process."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import parity_util as pu
+for name in ("s_224_S_forced", "s_280_L_forced"):
+    case, sd, bm, x, K, idx = pu.build_inputs(name)
+    gold = pu.load_golden(name)
+    m = pu.build_engine(case, sd, bm)
+    out = m(x, idx=idx, K=K, is_training=True)
+    bad = pu.compare(out, gold, [k for k in gold if k != "idx"], focal=float(K[:, 0, 0].max()))
+    assert not bad, (name, bad)
+    assert m.last_launch_count() > 0
+print("separate-LN ok")
+''' % (root, os.path.join(root, "tests"))
+    env = dict(os.environ, MHMR_LN_FOLD="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "separate-LN ok" in r.stdout, (r.stdout[-1000:], r.stderr[-2000:])
