@@ -6,8 +6,8 @@
 // Same arithmetic as dinov2 Block.forward (reached from reference blocks/dinov2.py:25) for the few rows that the
 // per-person outputs are sensitive to.
 //
-// x and h are written and re-read across grid barriers by different SMs: they are read with ld.global.cg (L2), never
-// through the (incoherent) L1.
+// x and h are written and re-read across grid barriers by different SMs: the rows are staged into shared memory by bulk
+// copies (async proxy, L2) and single elements are read with ld.global.cg, never through the (incoherent) L1.
 //
 // The first version launched three skinny linears per block: 74 dependent launches of ~20 us (latency chains, not
 // bandwidth: 2.1 ms of a 39.5 ms step).  Here
@@ -193,7 +193,22 @@ __device__ __forceinline__ void cta_linear(const float* __restrict__ W, int64_t 
     const int n = n0 + 4 * g + c;
     if (n < Nout) epi(n, j, v);
   }
+  fence_proxy_async_smem();   // this CTA's generic-proxy writes of the staged rows precede the next bulk copy into them
   __syncthreads();
+}
+
+// Row staging of the chain: every CTA needs ALL staged rows (8 x D for fc1, 8 x 4D for fc2).  One thread fetches them
+// with bulk copies (one round trip, no load instructions; per-thread ld.global.cg loops cost 6 k of the 42 k clk of a
+// block at 8 persons, `tools/gpu_trace_chain.sh`).  Caller: after a __syncthreads that follows the last read of `dst`
+// and, when `src` was written by other CTAs of this launch, after the grid barrier.
+__device__ __forceinline__ void bulk_rows(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = min(32768u, bytes - off);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(reinterpret_cast<char*>(dst) + off)),
+                 "l"(reinterpret_cast<const char*>(src) + off), "r"(n), "r"(smem_u32(bar))
+                 : "memory");
+  }
 }
 
 // ---- (B) the MLP chain of every block in one persistent cooperative kernel
@@ -205,8 +220,15 @@ refine_mlp_chain_kernel(const RefineLayer* __restrict__ layers, int depth, const
   float* xs = dyn;                 // [8][H] (phase 2) / [8][D] (phase 1)
   float* red = dyn + kPT * H;      // [8 warps][256]
   __shared__ float stats[kPT][2];
+  __shared__ __align__(8) uint64_t rbar;   // staged rows have landed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
+  uint32_t rpar = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&rbar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
   // fixed column ownership: fc1 (4D outputs) in slices of 32 per CTA, fc2 (D outputs) in slices of 8 per CTA,
   // both strided over the grid
   const int P = *count;
@@ -217,12 +239,23 @@ refine_mlp_chain_kernel(const RefineLayer* __restrict__ layers, int depth, const
     // ---------------- phase 1: h = gelu(W_fc1 . LN2(x + term_l) + b_fc1)
     for (int p0 = 0; p0 < P; p0 += kPT) {
       const int np = min(kPT, P - p0);
-      for (int idx = threadIdx.x; idx < kPT * (D >> 2); idx += kChainThreads) {   // raw rows x + term
+      // raw rows x and term_l: two bulk fetches into xs[0 : 8D) and xs[8D : 16D), summed in place
+      if (threadIdx.x == 0) {
+        // x was written through the generic proxy by other CTAs; xs by this CTA's threads (fenced below)
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const uint32_t rb = static_cast<uint32_t>(np) * D * 4u;
+        mbar_arrive_expect_tx(&rbar, 2u * rb);
+        bulk_rows(xs, x + static_cast<int64_t>(p0) * D, rb, &rbar);
+        bulk_rows(xs + kPT * D, tl + static_cast<int64_t>(p0) * D, rb, &rbar);
+      }
+      mbar_wait(&rbar, rpar);
+      rpar ^= 1u;
+      for (int idx = threadIdx.x; idx < kPT * (D >> 2); idx += kChainThreads) {
         const int j = idx / (D >> 2), k = 4 * (idx - j * (D >> 2));
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < np) {
-          const float4 a = __ldcg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(p0 + j) * D + k));
-          const float4 t = *reinterpret_cast<const float4*>(tl + static_cast<int64_t>(p0 + j) * D + k);
+          const float4 a = *reinterpret_cast<const float4*>(xs + j * D + k);
+          const float4 t = *reinterpret_cast<const float4*>(xs + (kPT + j) * D + k);
           v = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
         }
         *reinterpret_cast<float4*>(xs + j * D + k) = v;
@@ -264,13 +297,18 @@ refine_mlp_chain_kernel(const RefineLayer* __restrict__ layers, int depth, const
     // ---------------- phase 2: x = (x + term_l) + ls2 * (W_fc2 . h + b_fc2)
     for (int p0 = 0; p0 < P; p0 += kPT) {
       const int np = min(kPT, P - p0);
-      for (int idx = threadIdx.x; idx < kPT * (H >> 2); idx += kChainThreads) {
-        const int j = idx / (H >> 2), k = 4 * (idx - j * (H >> 2));
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < np) v = __ldcg(reinterpret_cast<const float4*>(h + static_cast<int64_t>(p0 + j) * H + k));
-        *reinterpret_cast<float4*>(xs + j * H + k) = v;
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");   // h was written through the generic proxy by other CTAs
+        const uint32_t rb = static_cast<uint32_t>(np) * H * 4u;
+        mbar_arrive_expect_tx(&rbar, rb);
+        bulk_rows(xs, h + static_cast<int64_t>(p0) * H, rb, &rbar);
       }
-      __syncthreads();
+      if (np < kPT)   // rows beyond the last person: zeros (generic proxy, disjoint from the copy)
+        for (int idx = threadIdx.x + np * (H >> 2); idx < kPT * (H >> 2); idx += kChainThreads)
+          *reinterpret_cast<float4*>(xs + 4 * idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(&rbar, rpar);
+      rpar ^= 1u;
+      if (np < kPT) __syncthreads();
       for (int cb = blockIdx.x; cb * 8 < D; cb += G) {
         const int ngroups = min(2, (D - cb * 8 + 3) / 4);
         cta_linear(L.Wfc2, H, D, H, cb * 8, ngroups, xs, H, red, warp, lane, [&](int n, int j, float v) {
