@@ -1,5 +1,5 @@
 """Turns the ncu exports brought back in gpurun_out/ into the committed summaries under profiles/.
-  python tools/summarize_profiles.py <tag> <launch-list csv> <ncu-rep with --set full>"""
+  python tools/summarize_profiles.py <tag> <launch-list csv> <ncu-rep with --set full>[,<ncu-rep>...]"""
 import collections
 import csv
 import os
@@ -36,8 +36,15 @@ with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as fh:
     for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         fh.write(f"| `{k}` | {n} | {v:.1f} | {100 * v / tot:.1f}% |\n")
 
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
+rows = []
+for one in rep.split(","):   # several captures of the same command: same columns, concatenate the launches
+    raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    part = list(csv.reader(raw.splitlines()))
+    if not rows:
+        rows = part
+    else:
+        assert part[0] == rows[0], "captures with different metric sets"
+        rows += part[2:]
 ix = {h: i for i, h in enumerate(rows[0])}
 cols = [("gpu__time_duration.sum", "us"), ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
         ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu %"),
@@ -68,7 +75,9 @@ with open(os.path.join(out_dir, f"{tag}_kernels_full.md"), "w") as fh:
 import json
 
 fam = {"attn_fwd_kernel": "attention", "gemm_tc2_kernel<0>": "gemm_qkv", "gemm_tc2_kernel<1>": "gemm_fc1",
-       "gemm_tc2_kernel<3>": "gemm_proj"}
+       "gemm_tc2_kernel<3>": "gemm_proj",
+       # LayerNorm folded into the GEMMs (default): qkv / fc1 consumers, proj / fc2 on the split residual stream
+       "gemm_tc2_kernel<7>": "gemm_qkv", "gemm_tc2_kernel<8>": "gemm_fc1", "gemm_tc2_kernel<6>": "gemm_proj"}
 traffic = {"_source": f"profiles/{tag}_kernels_full.md (ncu --set full --clock-control none, first captured launch of each "
                       f"kernel, multiHMR_896_L batch 8)"}
 seen = set()
