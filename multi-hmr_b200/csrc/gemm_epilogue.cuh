@@ -96,9 +96,40 @@ __device__ __forceinline__ void unpack_half8(const uint4& u, float (&f)[8]) {
   }
 }
 
+// Residual prefetch of the split-stream epilogue.  The epilogue of attn.proj is bound by the round trips of its residual
+// reads (ncu r02j: 42 % of the stall samples on the long scoreboard, 3 TB/s of traffic with ~32 KB in flight per SM):
+// each lane fetches the (hi, lo) values of the NEXT chunk it will process with cp.async into a per-warp 4 KB buffer
+// (slot (plane, k) at 512 B, lane at 16 B: a lane only ever reads back what it fetched itself, so no warp sync), issued
+// right after the current chunk's values have been read out, one whole chunk (TMEM load, transpose, math, stores) ahead.
+constexpr int kPrefetchBytes = 2 * 4 * 32 * 16;   // per epilogue warp
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_prefetch_resid(uint8_t* pre, const GemmEpi& ep, int M, int m_base, int n0,
+                                                        int lane) {
+  if constexpr (EPI == EPI_LS_RESID_SPLIT) {
+    const int cg = lane & 3, rs = lane >> 2;
+    const int n = n0 + cg * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int m = m_base + k * 8 + rs;
+      if (m < M) {
+        const int64_t off = static_cast<int64_t>(m) * ep.ldx16 + n;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(pre + (k * 32 + lane) * 16)),
+                     "l"(ep.x16 + off)
+                     : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(pre + ((4 + k) * 32 + lane) * 16)),
+                     "l"(ep.xlo + off)
+                     : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* scratch, const GemmEpi& ep,
-                                               int M, int N, int m_base, int n0, int lane, EpiRowState& st) {
+                                               int M, int N, int m_base, int n0, int lane, EpiRowState& st,
+                                               uint8_t* pre = nullptr, int next_m_base = 0, int next_n0 = -1) {
   constexpr bool kLn = epi_is_ln_consumer<EPI>();
   constexpr bool kF16 = (EPI == EPI_BIAS_F16 || EPI == EPI_BIAS_GELU_F16 || EPI == EPI_BIAS_RELU_F16 || kLn);
   constexpr bool kResid = (EPI == EPI_LS_RESID_F32);
@@ -120,14 +151,26 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
     *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
     *reinterpret_cast<float4*>(gg + 4) = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
     uint4 hi[4], lo[4];
+    if (pre != nullptr) {
+      // this chunk's values were fetched one chunk ago; read them out, then let the next chunk's fetch fly
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int m = m_base + k * 8 + rs;
-      const int64_t off = static_cast<int64_t>(m) * ep.ldx16 + n;
-      hi[k] = lo[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (m < M) {
-        hi[k] = *reinterpret_cast<const uint4*>(ep.x16 + off);
-        lo[k] = *reinterpret_cast<const uint4*>(ep.xlo + off);
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = (m_base + k * 8 + rs) < M;
+        hi[k] = ok ? *reinterpret_cast<const uint4*>(pre + (k * 32 + lane) * 16) : make_uint4(0u, 0u, 0u, 0u);
+        lo[k] = ok ? *reinterpret_cast<const uint4*>(pre + ((4 + k) * 32 + lane) * 16) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (next_n0 >= 0) epilogue_prefetch_resid<EPI>(pre, ep, M, next_m_base, next_n0, lane);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int m = m_base + k * 8 + rs;
+        const int64_t off = static_cast<int64_t>(m) * ep.ldx16 + n;
+        hi[k] = lo[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (m < M) {
+          hi[k] = *reinterpret_cast<const uint4*>(ep.x16 + off);
+          lo[k] = *reinterpret_cast<const uint4*>(ep.xlo + off);
+        }
       }
     }
 #pragma unroll

@@ -25,11 +25,18 @@ constexpr int BN2 = 256;   // columns per pair tile (each CTA stages 128 weight 
 constexpr int BK2 = 64;
 constexpr int kEpiWarps2 = 8;
 constexpr int kThreads2 = 128 + 32 * kEpiWarps2;
-constexpr int kStages2 = 5;
 constexpr int kABytes2 = 128 * BK2 * 2;         // 16 KB: this CTA's A rows
 constexpr int kBBytes2 = (BN2 / 2) * BK2 * 2;   // 16 KB: this CTA's half of the B tile
 constexpr int kStageBytes2 = kABytes2 + kBBytes2;
-constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + kEpiWarps2 * kScratchBytes + 256 + 1024;
+// smem ring depth: 5 stages.  PRE (attn.proj on the split stream: short K, epilogue-bound) trades one stage for the
+// residual prefetch buffers of its epilogue warps; mlp.fc2 (K = 4D, tensor-bound) keeps 5 stages and direct loads
+// (measured: fc2 +16 us per launch with 4 stages).
+template <bool PRE>
+constexpr int stages2() { return PRE ? 4 : 5; }
+template <bool PRE>
+constexpr int smem_bytes2() {
+  return stages2<PRE>() * kStageBytes2 + kEpiWarps2 * kScratchBytes + 256 + 1024 + (PRE ? kEpiWarps2 * kPrefetchBytes : 0);
+}
 constexpr int kTmemCols2 = 2 * BN2;              // 512
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address
 
@@ -91,10 +98,11 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
                : "memory");
 }
 
-template <int EPI>
+template <int EPI, bool PRE = false>
 __global__ void __launch_bounds__(kThreads2, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 int M, int N, int K, GemmEpi ep) {
+  constexpr int kStages2 = stages2<PRE>();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (128B swizzle atoms) by POINTER arithmetic, so that the compiler keeps the
   // shared address space (a round trip through uintptr_t degrades every access to generic LD/ST)
@@ -106,6 +114,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tfull_bar = bars + 2 * kStages2;   // [2]         MMA (multicast commit) -> this CTA's epilogue
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]         used in the leader: both epilogues -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* prefetch_base = reinterpret_cast<uint8_t*>(bars) + 256;   // [kEpiWarps2][kPrefetchBytes] (EPI_LS_RESID_SPLIT)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -230,6 +239,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int m_off = static_cast<int>(rank) * 128 + ew * 32;
     EpiStatsPrefetch pf;
     if (pair < num_tiles) epilogue_load_row_stats<EPI>(pf, ep, M, (pair / num_n) * BM2 + m_off, lane);
+    uint8_t* pre = PRE ? prefetch_base + (warp - 4) * kPrefetchBytes : nullptr;
+    if (PRE && pair < num_tiles)   // residual values of this warp's first chunk: in flight under the first main loop
+      epilogue_prefetch_resid<EPI>(pre, ep, M, (pair / num_n) * BM2 + m_off, (pair % num_n) * BN2 + par * 32, lane);
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++acc_iter) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const uint32_t as = acc_iter & 1u;
@@ -258,7 +270,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         const int n0 = n_blk * BN2 + c * 32;
-        if (n0 < N) epilogue_chunk<EPI>(r, scratch, ep, M, N, m_base, n0, lane, rowst);
+        // next chunk of this warp: same tile, or the first chunk of its next tile
+        int next_m = m_base, next_n0 = n0 + (kEpiWarps2 / 4) * 32;
+        if (ci == kChunksPerWarp - 1) {
+          const int nt = tile + num_pairs;
+          next_m = (nt / num_n) * BM2 + m_off;
+          next_n0 = (nt < num_tiles) ? (nt % num_n) * BN2 + par * 32 : -1;
+        }
+        if (n0 < N) epilogue_chunk<EPI>(r, scratch, ep, M, N, m_base, n0, lane, rowst, pre, next_m, next_n0);
       }
       epilogue_tile_end<EPI>(rowst, ep, M, m_base, n_blk * (kEpiWarps2 / 4) + par, lane);
     }
@@ -272,17 +291,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int EPI>
-int launch_2cta(const GemmPlan* p, cudaStream_t stream) {
-  auto kern = gemm_tc2_kernel<EPI>;
+template <int EPI, bool PRE>
+int launch_2cta_pre(const GemmPlan* p, cudaStream_t stream) {
+  auto kern = gemm_tc2_kernel<EPI, PRE>;
   static PerDeviceOnce once;
   if (once.first()) {
-    MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    MHMR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2<PRE>()));
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p->grid);
   cfg.blockDim = dim3(kThreads2);
-  cfg.dynamicSmemBytes = kSmemBytes2;
+  cfg.dynamicSmemBytes = smem_bytes2<PRE>();
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -295,6 +314,14 @@ int launch_2cta(const GemmPlan* p, cudaStream_t stream) {
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   MHMR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p->tmA, p->tmB, p->M, p->N, p->K, p->ep));
   return MHMR_OK;
+}
+
+template <int EPI>
+int launch_2cta(const GemmPlan* p, cudaStream_t stream) {
+  if constexpr (EPI == EPI_LS_RESID_SPLIT) {
+    if (p->K <= p->N) return launch_2cta_pre<EPI, true>(p, stream);   // attn.proj: K = N = D
+  }
+  return launch_2cta_pre<EPI, false>(p, stream);
 }
 
 }  // namespace
