@@ -160,6 +160,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
         hi[k] = ok ? *reinterpret_cast<const uint4*>(pre + (k * 32 + lane) * 16) : make_uint4(0u, 0u, 0u, 0u);
         lo[k] = ok ? *reinterpret_cast<const uint4*>(pre + ((4 + k) * 32 + lane) * 16) : make_uint4(0u, 0u, 0u, 0u);
       }
+      // the reads above are performed before the asynchronous refill of the same slots (same lane): a warp barrier
+      // orders them explicitly instead of relying on the in-order load/store unit
+      __syncwarp();
       if (next_n0 >= 0) epilogue_prefetch_resid<EPI>(pre, ep, M, next_m_base, next_n0, lane);
     } else {
 #pragma unroll
