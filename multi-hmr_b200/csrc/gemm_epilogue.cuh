@@ -99,7 +99,7 @@ __device__ __forceinline__ void unpack_half8(const uint4& u, float (&f)[8]) {
 // Residual prefetch of the split-stream epilogue.  The epilogue of attn.proj is bound by the round trips of its residual
 // reads (ncu r02j: 42 % of the stall samples on the long scoreboard, 3 TB/s of traffic with ~32 KB in flight per SM):
 // each lane fetches the (hi, lo) values of the NEXT chunk it will process with cp.async into a per-warp 4 KB buffer
-// (slot (plane, k) at 512 B, lane at 16 B: a lane only ever reads back what it fetched itself, so no warp sync), issued
+// (slot (plane, k) at 512 B, lane at 16 B: a lane only ever reads back what it fetched itself), issued
 // right after the current chunk's values have been read out, one whole chunk (TMEM load, transpose, math, stores) ahead.
 constexpr int kPrefetchBytes = 2 * 4 * 32 * 16;   // per epilogue warp
 
